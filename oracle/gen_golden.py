@@ -1,0 +1,206 @@
+"""Generate the golden bundles under tests/golden/ by running the LIVE, UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+The reference holds no golden vectors of its own, so these bundles -- inputs, recorded
+RNG draws, outputs, autograd gradients of the reference itself -- are what pins oracle/css_oracle.py.
+Each bundle is a small .npz; the GPU box only ever reads the committed files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_harness import load_reference, DrawRecorder, StubNet  # noqa: E402
+from css_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()      # copy: .numpy() aliases tensors that are updated in place later
+
+
+def loss_case(name, *, B2, C, h, w, Q, Nn, temp, strong, alpha, seed, strategy, protos, steps=1, tweak=None,
+              block=8):
+    """Contrast_Loss.forward + backward of the reference (loss.py:66-149) on synthetic inputs, `steps` times with
+    the prototypes carried over (first-touch branch, then EMA branch)."""
+    L, M, U = load_reference()
+    crit = L.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=strong, alpha=alpha)
+    out = dict(B2=B2, C=C, h=h, w=w, Q=Q, Nn=Nn, temp=temp, strong=strong, alpha=alpha, steps=steps, block=block)
+    prototypes = protos.clone()
+    for s in range(steps):
+        d = synth.student_batch(B2, C, h, w, seed=seed + s, strategy=strategy, block=block)
+        if strategy in ("mix", "cross"):
+            # prob_all as Model_mix/Model_cross compute it from the *incoming* prototypes (ddp_model.py:147-154)
+            xn = F.normalize(d["rep"].permute(0, 2, 3, 1), dim=-1).reshape(-1, d["rep"].shape[1])
+            pn = F.normalize(prototypes, dim=-1).permute(1, 0)
+            d["prob"] = F.softmax(torch.mm(xn, pn).reshape(B2, h, w, C).permute(0, 3, 1, 2) / temp, dim=1).contiguous()
+        if tweak is not None:
+            tweak(d, s)
+        rep = d["rep"].clone().requires_grad_(True)
+        torch.manual_seed(seed + 1000 + s)
+        np.random.seed(seed + 2000 + s)
+        rec = DrawRecorder()
+        proto_in = prototypes.clone()
+        with rec.recording():
+            loss = crit(rep, d["label"], d["mask"], d["prob"], prototypes)
+        loss.backward()
+        out.update({
+            f"s{s}_rep": _np(d["rep"]), f"s{s}_label": _np(d["label"]).astype(np.uint8),
+            f"s{s}_mask": _np(d["mask"]).astype(np.uint8), f"s{s}_prob": _np(d["prob"]),
+            f"s{s}_proto_in": _np(proto_in), f"s{s}_proto_out": _np(prototypes),
+            f"s{s}_loss": np.float32(loss.item()), f"s{s}_grad": _np(rep.grad),
+            f"s{s}_torch_seed": seed + 1000 + s, f"s{s}_numpy_seed": seed + 2000 + s,
+            f"s{s}_n_scored": len(rec.anchor_idx),
+        })
+        for k, (a, c, n) in enumerate(zip(rec.anchor_idx, rec.samp_class, rec.neg_idx)):
+            out[f"s{s}_anchor_idx_{k}"] = a.astype(np.int32)
+            out[f"s{s}_samp_class_{k}"] = c.astype(np.uint8)
+            out[f"s{s}_neg_idx_{k}"] = n.astype(np.int32)
+        print(f"  {name} step {s}: loss={loss.item():.6f} scored={len(rec.anchor_idx)} |grad|={rep.grad.abs().sum().item():.4f}")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def _passthrough2(images, labels, logits_1=None, logits_2=None, **kw):
+    return images, labels, logits_1, logits_2
+
+
+def _passthrough3(images, l1, l2, logits_1=None, logits_2=None, **kw):
+    return images, l1, l2, logits_1, logits_2
+
+
+def _passthrough1(images, labels, logits=None, **kw):
+    return images, labels, logits
+
+
+def stage12_case(name, *, kind, B, C, h, w, H, W, temp, seed, zero_rows=()):
+    """Model_mix / Model_cross / Model_ori_pseudo.forward of the reference with a stub network and pass-through
+    augmentation, so exactly ddp_model.py:101-118,147-154 (mix), :186-199,230-237 (cross), :34-37 (ori) execute."""
+    L, M, U = load_reference()
+    import torchvision.models as models
+    cfg = {"Dataset": {"crop_size": (H, W), "scale_size": (1.0, 1.0), "mix_mode": "none"}}
+    t = synth.teacher_batch(B, C, h, w, seed=seed)
+    s = synth.student_batch(2 * B, C, h, w, seed=seed + 1)
+    protos = 0.5 * t["centers"] + 0.3 * synth.warm_prototypes(C, seed=seed)
+    for r in zero_rows:
+        protos[r] = 0
+    pred_l_t = synth.logits_for(synth.class_map(B, C, h, w, synth._gen(seed + 5)), C, synth._gen(seed + 6))
+    rep_l_t = torch.randn(B, 256, h, w, generator=synth._gen(seed + 8))
+    img_l = torch.zeros(B, 3, H, W)
+    img_u = torch.zeros(B, 3, H, W)
+    ema = StubNet([(pred_l_t, rep_l_t), (t["pred_u"], t["rep_u"])])
+    stu = StubNet([(s["logits"][:B], s["rep"][:B]), (s["logits"][B:], s["rep"][B:])])
+    saved = (M.batch_transform, M.batch_transform_2, M.batch_transform_3,
+             M.generate_cut_gather, M.generate_cut_gather_2, M.generate_cut_gather_3)
+    M.batch_transform, M.batch_transform_2, M.batch_transform_3 = _passthrough1, _passthrough2, _passthrough3
+    M.generate_cut_gather = lambda a, b, c, mode=None: (a, b, c)
+    M.generate_cut_gather_2 = lambda a, b, c, d, mode=None: (a, b, c, d)
+    M.generate_cut_gather_3 = lambda a, b, c, d, e, mode=None: (a, b, c, d, e)
+    try:
+        out = dict(kind=kind, B=B, C=C, h=h, w=w, H=H, W=W, temp=temp,
+                   rep_u=_np(t["rep_u"]), pred_u=_np(t["pred_u"]), prototypes=_np(protos),
+                   rep_all=_np(s["rep"]), pred_all=_np(s["logits"]))
+        if kind == "mix":
+            m = M.Model_mix(models.resnet18(), num_classes=C, output_dim=256, config=cfg, temp=temp)
+            m.model, m.ema_model = stu, ema
+            r = m(img_l, img_u, protos)
+            out.update(fused=_np(r[2]), conf_cls=_np(r[3]), conf_rep=_np(r[4]), prob_all=_np(r[6]))
+        elif kind == "cross":
+            m = M.Model_cross(models.resnet18(), num_classes=C, output_dim=256, config=cfg, temp=temp)
+            m.model, m.ema_model = stu, ema
+            r = m(img_l, img_u, protos)
+            out.update(label_cls=_np(r[2]), label_rep=_np(r[3]), conf_cls=_np(r[4]), conf_rep=_np(r[5]),
+                       prob_all=_np(r[7]))
+        else:
+            m = M.Model_ori_pseudo(models.resnet18(), num_classes=C, output_dim=256, config=cfg)
+            m.model, m.ema_model = stu, StubNet([(t["pred_u"], t["rep_u"])])
+            r = m(img_l, img_u)
+            out.update(label_cls=_np(r[2]), conf_cls=_np(r[3]), pred_u_large_raw=_np(r[6]))
+        # the up-sampled similarity map itself (ddp_model.py:111), recomputed with the same torch calls, so the
+        # oracle's bilinear restatement and the near-tie margins can be checked directly
+        xn = F.normalize(t["rep_u"].permute(0, 2, 3, 1), dim=-1).reshape(-1, 256)
+        sim = torch.mm(xn, F.normalize(protos, dim=-1).permute(1, 0)).reshape(B, h, w, C).permute(0, 3, 1, 2)
+        out.update(sim=_np(sim), sim_large=_np(F.interpolate(sim, size=(H, W), mode="bilinear", align_corners=True)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(f"  {name}: ok ({kind})")
+    finally:
+        (M.batch_transform, M.batch_transform_2, M.batch_transform_3,
+         M.generate_cut_gather, M.generate_cut_gather_2, M.generate_cut_gather_3) = saved
+
+
+def glue_case(name, *, strategy, B, C, H, W, h, w, weak, seed):
+    """The no_grad glue block of train(): mix_label.py:175-183 / cross_label.py:178-185 / ori_pseudo.py:171-178.
+    The scripts cannot be imported (`shutup` missing, and the block is inline in train()), so the same statements
+    are executed here with the reference's own label_onehot / label_onehot_2 (utils.py:116-136)."""
+    L, M, U = load_reference()
+    g = synth._gen(seed)
+    train_l_label = synth.class_map(B, C, H, W, g, ignore_frac=0.1, block=16)
+    u_label = synth.class_map(B, C, H, W, g, ignore_frac=0.2, block=16)
+    conf = torch.rand(B, H, W, generator=g)
+    conf = torch.floor(conf * 255) / 255           # 8-bit quantised as after the PIL round trip (VOC.py:289-290)
+    with torch.no_grad():
+        u_mask = conf.ge(weak).float()
+        mask_all = torch.cat(((train_l_label.unsqueeze(1) >= 0).float(), u_mask.unsqueeze(1)))
+        mask_all = F.interpolate(mask_all, size=(h, w), mode="nearest")
+        label_l = F.interpolate(U.label_onehot(train_l_label, C), size=(h, w), mode="nearest")
+        if strategy == "mix":
+            label_u = F.interpolate(U.label_onehot_2(u_label, C), size=(h, w), mode="nearest")[:, 1:]
+        else:
+            label_u = F.interpolate(U.label_onehot(u_label, C), size=(h, w), mode="nearest")
+        label_all = torch.cat((label_l, label_u))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), strategy=strategy, C=C, weak=weak, h=h, w=w,
+                        train_l_label=_np(train_l_label).astype(np.int16), u_label=_np(u_label).astype(np.int16),
+                        conf=_np(conf), mask_all=_np(mask_all).astype(np.uint8),
+                        label_all=_np(label_all).astype(np.uint8))
+    print(f"  {name}: ok")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    D = 256
+    zeros = lambda C: torch.zeros(C, D)  # noqa: E731
+
+    print("loss cases")
+    # first-touch then EMA (two steps, prototypes carried over), ori_pseudo-style prob
+    loss_case("loss_ori_c5", B2=2, C=5, h=9, w=9, Q=8, Nn=16, temp=0.5, strong=0.97, alpha=0.99, seed=11,
+              strategy="ori", protos=zeros(5), steps=2)
+    # VOC class count, ragged map, mix-style labels (all-zero rows on ignored pixels), prob from prototypes
+    loss_case("loss_mix_c21", B2=2, C=21, h=13, w=11, Q=16, Nn=32, temp=0.5, strong=0.8, alpha=0.99, seed=23,
+              strategy="mix", protos=synth.warm_prototypes(21, seed=23, zero_rows=(3,)), steps=2, block=2)
+
+    # a present class without any hard pixel (skipped at loss.py:125-130 but counted in V), an absent class,
+    # and a lower strong threshold so that hard != valid
+    def tweak_nohard(d, s):
+        d["prob"][:, 2] = 0.99                       # class 2: valid but never hard
+        d["mask"][d["cls"].unsqueeze(1) == 4] = 0    # class 4: absent
+        d["prob"][:, 0] = torch.where(d["prob"][:, 0] > 0.5, torch.full_like(d["prob"][:, 0], 0.98), d["prob"][:, 0])
+    loss_case("loss_nohard_c7", B2=2, C=7, h=10, w=12, Q=12, Nn=24, temp=0.3, strong=0.9, alpha=0.9, seed=37,
+              strategy="ori", protos=synth.warm_prototypes(7, seed=37), steps=1, tweak=tweak_nohard, block=3)
+
+    # degenerate: a single class present -> loss 0 with dense zero grad (loss.py:116-117); prototypes still update
+    def tweak_single(d, s):
+        d["mask"][d["cls"].unsqueeze(1) != 1] = 0
+    loss_case("loss_single_c4", B2=1, C=4, h=8, w=8, Q=4, Nn=8, temp=0.5, strong=0.97, alpha=0.99, seed=41,
+              strategy="ori", protos=zeros(4), steps=1, tweak=tweak_single)
+    # CityScapes class count
+    loss_case("loss_cross_c19", B2=2, C=19, h=12, w=12, Q=16, Nn=48, temp=0.5, strong=0.8, alpha=0.99, seed=53,
+              strategy="cross", protos=synth.warm_prototypes(19, seed=53), steps=1, block=3)
+
+    print("stage 1/2 cases")
+    stage12_case("stage12_mix_c21", kind="mix", B=2, C=21, h=9, w=9, H=33, W=33, temp=0.5, seed=61, zero_rows=(5,))
+    stage12_case("stage12_cross_c19", kind="cross", B=1, C=19, h=7, w=10, H=25, W=37, temp=0.5, seed=67)
+    stage12_case("stage12_ori_c21", kind="ori", B=2, C=21, h=9, w=9, H=33, W=33, temp=0.5, seed=71)
+
+    print("glue cases")
+    glue_case("glue_mix", strategy="mix", B=2, C=21, H=33, W=33, h=9, w=9, weak=0.7, seed=81)
+    glue_case("glue_cross", strategy="cross", B=2, C=19, H=25, W=37, h=7, w=10, weak=0.7, seed=83)
+    glue_case("glue_ori", strategy="ori", B=1, C=21, H=40, W=40, h=10, w=10, weak=0.7, seed=87)
+
+
+if __name__ == "__main__":
+    main()
