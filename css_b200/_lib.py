@@ -1,0 +1,80 @@
+"""ctypes binding of libcss_b200.so (the C ABI declared in include/css_b200.h).
+
+There is NO fallback: if the library is missing and cannot be built, or an entry point returns non-zero, a
+RuntimeError is raised.  Nothing here imports `oracle`.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcss_b200.so")
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+SIM_COS, SIM_SOFTMAX = 0, 1
+FUSE_NONE, FUSE_MIX = 0, 1
+META_WORDS = 256
+META_V, META_N_VALID, META_N_HARD, META_CLS_OF_SLOT, META_SLOT_OF_CLS = 0, 32, 64, 96, 128
+CMAX = 32
+D = 256
+
+P = c_void_p
+# name -> (restype, argtypes); must list every symbol include/css_b200.h declares (tests/test_abi.py checks it)
+SIGNATURES = {
+    "css_version": (c_int, []),
+    "css_last_error": (ctypes.c_char_p, []),
+    "css_sm_count": (c_int, []),
+    "css_launch_count": (ctypes.c_ulonglong, []),
+    "css_sim_map": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "css_upsample_label_fuse": (c_int, [P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "css_select_tiles": (c_int, [c_int]),
+    "css_select": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "css_stream_blocks": (c_int, []),
+    "css_stream_rep": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, P, P, P]),
+    "css_sample": (c_int, [P, P, c_uint64, c_uint64, c_int, c_int, c_int, P, P, P]),
+    "css_score_ce": (c_int, [P, P, P, P, P, P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_int, c_int, c_int, c_float,
+                             P, P, P, P, P]),
+    "css_grad_scatter": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "css_threshold_glue": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (building first if the .so is absent and nvcc is available) and returns the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # no nvcc on this host
+            raise RuntimeError(
+                f"css_b200: {LIB_PATH} is missing and could not be built ({e}). "
+                "Run `python -m css_b200.build` (needs nvcc). There is no CPU fallback.") from e
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().css_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"css_b200.{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) CUDA tensor, None -> NULL."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,78 @@
+// Shared device/host helpers of libcss_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/css_b200.h"
+
+#define CSS_D 256            // feature width (reference: output_dim=256, mix_label.py:75,93)
+#define CSS_CMAX 32          // classes fit one 32-bit set per pixel
+#define CSS_SEL_TILE 256     // pixels per selection tile (= threads per block of the selection kernels)
+
+void css_set_error(const char* fmt, ...);
+
+#define CSS_CHECK_ARG(cond, code, ...)                  \
+    do {                                                \
+        if (!(cond)) {                                  \
+            css_set_error(__VA_ARGS__);                 \
+            return (code);                              \
+        }                                               \
+    } while (0)
+
+#define CSS_CHECK_LAUNCH(name, n_kernels)                                              \
+    do {                                                                               \
+        css_count_launches(n_kernels);                                                 \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            css_set_error("%s: %s", name, cudaGetErrorString(e__));                    \
+            return (int)e__;                                                           \
+        }                                                                              \
+    } while (0)
+
+static inline int css_check_dims(int C, int D) {
+    if (D != CSS_D) { css_set_error("D must be %d (got %d)", CSS_D, D); return CSS_E_DIM; }
+    if (C < 1 || C > CSS_CMAX) { css_set_error("C must be in [1,%d] (got %d)", CSS_CMAX, C); return CSS_E_DIM; }
+    return 0;
+}
+
+int css_cached_sm_count();
+void css_count_launches(int n);     // bookkeeping behind css_launch_count()
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming (read-once) loads: keep them out of L1
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator the device sampler is built on.
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __device__ __forceinline__ static uint4 run(uint4 c, uint2 k) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+            uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += W0;
+            k.y += W1;
+        }
+        return c;
+    }
+};
+#endif

@@ -1,0 +1,208 @@
+// Stage 3 selection: valid / hard class sets per pixel and their ORDER-PRESERVING per-class compaction, plus the fused
+// threshold glue that produces label_all / mask_all at representation resolution.
+// Reference: generalframeworks/loss/loss.py:80,94-99,111-113; mix_label.py:175-183; cross_label.py:178-185;
+// ori_pseudo.py:171-178; generalframeworks/utils.py:116-136.
+//
+// Compaction is a three-kernel stable counting sort (classify+count per 256-pixel tile -> exclusive scan over tiles ->
+// scatter with ballot ranks), because the reference's sampled indices are ranks in row-major order inside each class
+// list; an atomic-counter compaction would scramble them.
+#include "css_common.cuh"
+
+extern "C" int css_select_tiles(int N) { return (N + CSS_SEL_TILE - 1) / CSS_SEL_TILE; }
+
+// tile_counts layout: row r = kind*C + c (kind 0 = valid, 1 = hard), T entries per row.
+__global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const float* __restrict__ label, const float* __restrict__ mask,
+                                                                       const float* __restrict__ prob, float strong, int C, int hw,
+                                                                       int N, int T, uint32_t* __restrict__ valid_bits,
+                                                                       uint32_t* __restrict__ hard_bits, int32_t* __restrict__ tile_counts) {
+    __shared__ int cnt[2 * CSS_CMAX];
+    if (threadIdx.x < 2 * CSS_CMAX) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int p = blockIdx.x * CSS_SEL_TILE + threadIdx.x;
+    uint32_t vb = 0, hb = 0;
+    if (p < N) {
+        const int b = p / hw, s = p - b * hw;
+        const float m = __ldg(mask + p);
+        const float* lp = label + (size_t)b * C * hw + s;
+        const float* pp = prob + (size_t)b * C * hw + s;
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float l = ldg_stream(lp + (size_t)c * hw);
+            if (__fmul_rn(l, m) != 0.f) {                       // valid_pixel = label * mask (loss.py:80), .bool() (:99,:111)
+                vb |= 1u << c;
+                if (__ldg(pp + (size_t)c * hw) < strong) hb |= 1u << c;   // prob < strong_threshold (loss.py:99)
+            }
+        }
+        valid_bits[p] = vb;
+        hard_bits[p] = hb;
+    }
+    uint32_t uni = __reduce_or_sync(0xffffffffu, vb);
+    const int lane = threadIdx.x & 31;
+    while (uni) {
+        const int c = __ffs(uni) - 1;
+        uni &= uni - 1;
+        const int nv = __popc(__ballot_sync(0xffffffffu, (vb >> c) & 1u));
+        const int nh = __popc(__ballot_sync(0xffffffffu, (hb >> c) & 1u));
+        if (lane == 0) {
+            atomicAdd(&cnt[c], nv);
+            if (nh) atomicAdd(&cnt[CSS_CMAX + c], nh);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {
+        const int kind = threadIdx.x / C, c = threadIdx.x - kind * C;
+        tile_counts[(size_t)threadIdx.x * T + blockIdx.x] = cnt[kind * CSS_CMAX + c];
+    }
+}
+
+// One block: warp-per-row exclusive scan over the T tiles (in place), class totals and the present-class table into meta.
+__global__ void __launch_bounds__(1024) select_scan_kernel(int32_t* __restrict__ tile_counts, int C, int T, int32_t* __restrict__ meta) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < 2 * C; r += 32) {
+        int32_t* row = tile_counts + (size_t)r * T;
+        int running = 0;
+        for (int base = 0; base < T; base += 32) {
+            const int i = base + lane;
+            const int v = (i < T) ? row[i] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (i < T) row[i] = running + inc - v;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            const int kind = r / C, c = r - kind * C;
+            meta[(kind ? CSS_META_N_HARD : CSS_META_N_VALID) + c] = running;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int V = 0;
+        for (int c = 0; c < CSS_CMAX; ++c) {
+            if (c >= C) {
+                meta[CSS_META_N_VALID + c] = 0;
+                meta[CSS_META_N_HARD + c] = 0;
+            }
+            if (c < C && meta[CSS_META_N_VALID + c] > 0) {       // classes with no local valid pixel are skipped (loss.py:96-97)
+                meta[CSS_META_CLS_OF_SLOT + V] = c;
+                meta[CSS_META_SLOT_OF_CLS + c] = V++;
+            } else {
+                meta[CSS_META_SLOT_OF_CLS + c] = -1;
+            }
+        }
+        for (int k = V; k < CSS_CMAX; ++k) meta[CSS_META_CLS_OF_SLOT + k] = -1;
+        meta[CSS_META_V] = V;
+    }
+}
+
+__global__ void __launch_bounds__(CSS_SEL_TILE) select_scatter_kernel(const uint32_t* __restrict__ valid_bits, const uint32_t* __restrict__ hard_bits,
+                                                                      const int32_t* __restrict__ tile_off, int C, int N, int T,
+                                                                      int32_t* __restrict__ valid_list, int32_t* __restrict__ hard_list) {
+    __shared__ int wcnt[2][CSS_CMAX][CSS_SEL_TILE / 32];
+    for (int i = threadIdx.x; i < 2 * CSS_CMAX * (CSS_SEL_TILE / 32); i += CSS_SEL_TILE) (&wcnt[0][0][0])[i] = 0;
+    __syncthreads();
+    const int p = blockIdx.x * CSS_SEL_TILE + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t vb = (p < N) ? valid_bits[p] : 0u;
+    const uint32_t hb = (p < N) ? hard_bits[p] : 0u;
+    const uint32_t uni = __reduce_or_sync(0xffffffffu, vb);
+    for (uint32_t u = uni; u;) {
+        const int c = __ffs(u) - 1;
+        u &= u - 1;
+        const int nv = __popc(__ballot_sync(0xffffffffu, (vb >> c) & 1u));
+        const int nh = __popc(__ballot_sync(0xffffffffu, (hb >> c) & 1u));
+        if (lane == 0) {
+            wcnt[0][c][warp] = nv;
+            wcnt[1][c][warp] = nh;
+        }
+    }
+    __syncthreads();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t u = uni; u;) {
+        const int c = __ffs(u) - 1;
+        u &= u - 1;
+        const uint32_t bv = __ballot_sync(0xffffffffu, (vb >> c) & 1u);
+        const uint32_t bh = __ballot_sync(0xffffffffu, (hb >> c) & 1u);
+        int ov = 0, oh = 0;
+        for (int w2 = 0; w2 < warp; ++w2) {
+            ov += wcnt[0][c][w2];
+            oh += wcnt[1][c][w2];
+        }
+        if ((vb >> c) & 1u)
+            valid_list[(size_t)c * N + tile_off[(size_t)c * T + blockIdx.x] + ov + __popc(bv & lt)] = p;
+        if ((hb >> c) & 1u)
+            hard_list[(size_t)c * N + tile_off[(size_t)(C + c) * T + blockIdx.x] + oh + __popc(bh & lt)] = p;
+    }
+}
+
+extern "C" int css_select(const float* label, const float* mask, const float* prob, float strong_threshold, int B2, int C,
+                          int h, int w, uint32_t* valid_bits, uint32_t* hard_bits, int32_t* tile_counts, int32_t* valid_list,
+                          int32_t* hard_list, int32_t* meta, void* stream) {
+    CSS_CHECK_ARG(label && mask && prob && valid_bits && hard_bits && tile_counts && valid_list && hard_list && meta, CSS_E_ARG,
+                  "css_select: null pointer");
+    CSS_CHECK_ARG(B2 > 0 && h > 0 && w > 0, CSS_E_ARG, "css_select: non-positive size");
+    CSS_CHECK_ARG(C >= 1 && C <= CSS_CMAX, CSS_E_DIM, "css_select: C must be in [1,%d]", CSS_CMAX);
+    CSS_CHECK_ARG((long long)B2 * h * w * CSS_CMAX < (1ll << 31), CSS_E_SIZE, "css_select: too many pixels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = h * w, N = B2 * hw, T = css_select_tiles(N);
+    select_classify_kernel<<<T, CSS_SEL_TILE, 0, st>>>(label, mask, prob, strong_threshold, C, hw, N, T, valid_bits, hard_bits,
+                                                      tile_counts);
+    select_scan_kernel<<<1, 1024, 0, st>>>(tile_counts, C, T, meta);
+    select_scatter_kernel<<<T, CSS_SEL_TILE, 0, st>>>(valid_bits, hard_bits, tile_counts, C, N, T, valid_list, hard_list);
+    CSS_CHECK_LAUNCH("css_select", 3);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K0: weak-threshold mask + one-hot + nearest down-sampling in one pass.
+//   mask_all  = nearest(cat(label_l >= 0, conf_u >= weak))                         mix_label.py:176-178
+//   label_all = nearest(cat(onehot(relu(label_l)), onehot_u))                      mix_label.py:180-183
+//   mode 0: onehot_u = label_onehot(label_u) (relu, utils.py:116-125); mode 1: label_onehot_2(label_u)[:,1:] (utils.py:127-136)
+// Nearest source index as ATen: min(int(floorf(dst * (in/out))), in-1), scale in fp32.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) threshold_glue_kernel(const int64_t* __restrict__ label_l, const int64_t* __restrict__ label_u,
+                                                             const float* __restrict__ conf_u, float weak, int mode, int B, int C,
+                                                             int H, int W, int h, int w, float sy, float sx,
+                                                             float* __restrict__ label_all, float* __restrict__ mask_all) {
+    const int hw = h * w;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 2 * B * hw) return;
+    const int bb = p / hw, s = p - bb * hw;
+    const int y = s / w, x = s - y * w;
+    const int Y = min((int)floorf(__fmul_rn((float)y, sy)), H - 1);
+    const int X = min((int)floorf(__fmul_rn((float)x, sx)), W - 1);
+    int cls;
+    float m;
+    if (bb < B) {
+        const long long l = label_l[((size_t)bb * H + Y) * W + X];
+        m = (l >= 0) ? 1.f : 0.f;
+        cls = (int)max(l, 0ll);
+    } else {
+        const size_t o = ((size_t)(bb - B) * H + Y) * W + X;
+        const long long l = label_u[o];
+        m = (conf_u[o] >= weak) ? 1.f : 0.f;
+        cls = (mode == 1) ? (int)l : (int)max(l, 0ll);
+    }
+    mask_all[p] = m;
+    float* o = label_all + (size_t)bb * C * hw + s;
+    for (int c = 0; c < C; ++c) o[(size_t)c * hw] = (c == cls) ? 1.f : 0.f;
+}
+
+extern "C" int css_threshold_glue(const int64_t* label_l, const int64_t* label_u, const float* conf_u, float weak_threshold,
+                                  int mode, int B, int C, int H, int W, int h, int w, float* label_all, float* mask_all,
+                                  void* stream) {
+    CSS_CHECK_ARG(label_l && label_u && conf_u && label_all && mask_all, CSS_E_ARG, "css_threshold_glue: null pointer");
+    CSS_CHECK_ARG(B > 0 && H > 0 && W > 0 && h > 0 && w > 0, CSS_E_ARG, "css_threshold_glue: non-positive size");
+    CSS_CHECK_ARG(mode == 0 || mode == 1, CSS_E_ARG, "css_threshold_glue: bad mode %d", mode);
+    CSS_CHECK_ARG(C >= 1 && C <= CSS_CMAX, CSS_E_DIM, "css_threshold_glue: C must be in [1,%d]", CSS_CMAX);
+    CSS_CHECK_ARG(2ll * B * h * w * CSS_CMAX < (1ll << 31), CSS_E_SIZE, "css_threshold_glue: too many pixels");
+    const int n = 2 * B * h * w;
+    threshold_glue_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(label_l, label_u, conf_u, weak_threshold, mode, B, C,
+                                                                            H, W, h, w, (float)H / (float)h, (float)W / (float)w,
+                                                                            label_all, mask_all);
+    CSS_CHECK_LAUNCH("css_threshold_glue", 1);
+    return 0;
+}

@@ -1,0 +1,198 @@
+"""Contrast_Loss: drop-in for generalframeworks/loss/loss.py:66-149 running on the CUDA kernels of libcss_b200.
+
+Same constructor, same forward signature, same side effect (prototypes are updated IN PLACE before scoring and the
+updated prototype is the positive), same degenerate behaviour (exactly 0 with a dense zero gradient when fewer than
+two classes are present).  Differences, all opt-in or invisible to callers:
+  * no host synchronisation anywhere (counts, present classes, V live on the device);
+  * the 116 MB/rank all_gather of loss.py:77,81 is replaced by one all-reduce of [C, D+1] per-class sums/counts;
+  * sampling uses a device Philox stream; `forward(..., _indices=(anchor_idx, neg_idx))` feeds recorded draws
+    (e.g. the reference's) for bit-exact verification.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .ops import _cuda_f32
+
+
+class _Workspace:
+    """Scratch buffers of one problem shape, owned by the Python side (the library never allocates)."""
+
+    def __init__(self, B2, C, D, h, w, Q, Nn, device):
+        lib = _lib.load()
+        N = B2 * h * w
+        T = lib.css_select_tiles(N)
+        with torch.cuda.device(device):
+            G = lib.css_stream_blocks()
+        i32 = dict(device=device, dtype=torch.int32)
+        f32 = dict(device=device, dtype=torch.float32)
+        self.key = (B2, C, D, h, w, Q, Nn, str(device))
+        self.N, self.T, self.G = N, T, G
+        self.valid_bits = torch.empty(N, **i32)
+        self.hard_bits = torch.empty(N, **i32)
+        self.tile_counts = torch.empty(2 * C * T, **i32)
+        self.valid_list = torch.empty(C * N, **i32)
+        self.hard_list = torch.empty(C * N, **i32)
+        self.meta = torch.zeros(_lib.META_WORDS, **i32)
+        self.rows_hat = torch.empty(N * D, **f32)
+        self.norms = torch.empty(N, **f32)
+        self.partials = torch.empty(G * C * D, **f32)
+        self.touched = torch.empty(G, **i32)
+        self.class_stats = torch.empty(C, D + 1, **f32)
+        self.proto_hat = torch.empty(C * D, **f32)
+        self.class_cdf = torch.empty(_lib.CMAX * _lib.CMAX, **f32)
+        self.loss_kq = torch.empty(C * Q, **f32)
+
+
+def allreduce_class_stats(class_stats, group=None):
+    """Sum the [C, D+1] per-class (feature sums | counts) block over all ranks: the one exchange step of the path.
+    mean_c = sum_ranks(sums_c) / sum_ranks(count_c) equals the reference's mean over all_gather'ed rows
+    (loss.py:77-81,102).  No-op on a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(class_stats, op=dist.ReduceOp.SUM, group=group)
+    return class_stats
+
+
+class _ContrastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rep, label, mask, prob, prototypes, mod, indices, want_grad):
+        lib = _lib.load()
+        B2, D, h, w = rep.shape
+        C = label.shape[1]
+        Q, Nn = mod.num_queries, mod.num_negatives
+        dev = rep.device
+        ws = mod._workspace(B2, C, D, h, w, dev)
+        N = ws.N
+        st = stream_ptr()
+        check(lib.css_select(ptr(label), ptr(mask), ptr(prob), float(mod.strong_threshold), B2, C, h, w, ptr(ws.valid_bits),
+                             ptr(ws.hard_bits), ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), st),
+              "css_select")
+        check(lib.css_stream_rep(ptr(rep), _lib.DTYPE_F32, ptr(ws.valid_bits), ptr(ws.meta), B2, C, D, h, w, ptr(ws.rows_hat),
+                                 ptr(ws.norms), ptr(ws.partials), ptr(ws.touched), ptr(ws.class_stats), st), "css_stream_rep")
+        allreduce_class_stats(ws.class_stats, mod.process_group)
+        check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
+                                float(mod.temp), C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
+        if mod.sync_prototypes and dist.is_initialized() and dist.get_world_size(mod.process_group) > 1:
+            dist.broadcast(prototypes, src=dist.get_global_rank(mod.process_group, 0) if mod.process_group else 0,
+                           group=mod.process_group)
+        anchor_px = torch.empty(C * Q, device=dev, dtype=torch.int32)
+        grad_anchor = torch.empty(C * Q * D, device=dev, dtype=torch.float32) if want_grad else None
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        a_idx, n_idx = (None, None) if indices is None else indices
+        seed, offset = mod._next_draw_key()
+        check(lib.css_score_ce(ptr(ws.rows_hat), ptr(ws.norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+                               ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, N, C, D, Q, Nn,
+                               float(mod.temp), ptr(ws.loss_kq), ptr(anchor_px), ptr(grad_anchor), ptr(loss), st), "css_score_ce")
+        ctx.shape = (B2, D, h, w)
+        ctx.n_anchor = C * Q
+        ctx.save_for_backward(anchor_px, grad_anchor)
+        mod.last = dict(ws=ws, anchor_px=anchor_px, grad_anchor=grad_anchor, seed=seed, offset=offset)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        anchor_px, grad_anchor = ctx.saved_tensors
+        if grad_anchor is None:
+            raise RuntimeError("css_b200: Contrast_Loss backward without forward-time gradient state")
+        B2, D, h, w = ctx.shape
+        lib = _lib.load()
+        go = grad_out.detach().to(torch.float32).contiguous()
+        grad_rep = torch.empty(ctx.shape, device=anchor_px.device, dtype=torch.float32)
+        with torch.cuda.device(anchor_px.device):
+            check(lib.css_grad_scatter(ptr(go), ptr(anchor_px), ptr(grad_anchor), ctx.n_anchor, B2, D, h, w, ptr(grad_rep),
+                                       stream_ptr()), "css_grad_scatter")
+        return grad_rep, None, None, None, None, None, None, None
+
+
+class Contrast_Loss(nn.Module):
+    """Same constructor and forward as the reference's Contrast_Loss (loss.py:66-75)."""
+
+    def __init__(self, num_queries, num_negatives, temp=0.5, mean=False, strong_threshold=0.97, alpha=0.99,
+                 seed=None, process_group=None, sync_prototypes=False):
+        super().__init__()
+        self.temp = temp
+        self.mean = mean                      # unused by the reference as well (loss.py:70)
+        self.num_queries = num_queries
+        self.num_negatives = num_negatives
+        self.strong_threshold = strong_threshold
+        self.alpha = alpha
+        self.process_group = process_group
+        self.sync_prototypes = sync_prototypes   # extension, default off: the reference lets per-rank prototypes drift
+        self._seed = seed
+        self._step = 0
+        self._ws = None
+        self.last = None
+
+    # ---- sampler state: (seed, offset) of the device Philox stream; one offset per forward call -------------------
+    def set_sampler(self, seed, step=0):
+        self._seed, self._step = int(seed), int(step)
+
+    def _next_draw_key(self):
+        if self._seed is None:   # derived from torch's CPU generator so torch.manual_seed() makes runs reproducible
+            self._seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            if dist.is_available() and dist.is_initialized():
+                self._seed ^= 0x9E3779B97F4A7C15 * (dist.get_rank() + 1) & (2 ** 63 - 1)
+        off = self._step
+        self._step += 1
+        return self._seed & (2 ** 64 - 1), off
+
+    def _workspace(self, B2, C, D, h, w, device):
+        key = (B2, C, D, h, w, self.num_queries, self.num_negatives, str(device))
+        if self._ws is None or self._ws.key != key:
+            self._ws = _Workspace(B2, C, D, h, w, self.num_queries, self.num_negatives, device)
+        return self._ws
+
+    def forward(self, rep, label, mask, prob, prototypes, _indices=None):
+        """rep [B2,256,h,w], label [B2,C,h,w], mask [B2,1,h,w], prob [B2,C,h,w], prototypes [C,256] (updated in place).
+        _indices: optional (anchor_idx int32 [C,Q], neg_idx int32 [C,Q,Nn]) slot-major device tensors of recorded draws."""
+        if not rep.is_cuda:
+            raise RuntimeError("css_b200: Contrast_Loss needs CUDA tensors (no CPU fallback)")
+        if rep.dtype != torch.float32:
+            raise RuntimeError(f"css_b200: rep must be float32, got {rep.dtype}")
+        if not (prototypes.is_cuda and prototypes.dtype == torch.float32 and prototypes.is_contiguous()):
+            raise RuntimeError("css_b200: prototypes must be a contiguous float32 CUDA tensor (it is updated in place)")
+        if rep.shape[1] != _lib.D or prototypes.shape != (label.shape[1], _lib.D):
+            raise RuntimeError("css_b200: rep must be [B2,256,h,w] and prototypes [C,256]")
+        if mask.shape[1] != 1 or label.shape != prob.shape or label.shape[0] != rep.shape[0] or label.shape[2:] != rep.shape[2:]:
+            raise RuntimeError("css_b200: label/prob must be [B2,C,h,w] and mask [B2,1,h,w] at rep resolution")
+        want_grad = torch.is_grad_enabled() and rep.requires_grad
+        rep_c = rep if rep.is_contiguous() else rep.contiguous()
+        label_c, mask_c, prob_c = _cuda_f32(label, "label"), _cuda_f32(mask, "mask"), _cuda_f32(prob, "prob")
+        if _indices is not None:
+            a, n = _indices
+            if not (a.is_cuda and n.is_cuda and a.dtype == torch.int32 and n.dtype == torch.int32):
+                raise RuntimeError("css_b200: _indices must be int32 CUDA tensors")
+            _indices = (a.contiguous(), n.contiguous())
+        with torch.cuda.device(rep.device):
+            return _ContrastFn.apply(rep_c, label_c, mask_c, prob_c, prototypes.detach(), self, _indices, want_grad)
+
+    # ---- verification helpers (read device state back: they synchronise, never used on the training path) --------------
+    def selection(self):
+        """Present classes, counts and the valid / hard pixel-id lists of the last forward, as Python objects."""
+        ws = self.last["ws"]
+        meta = ws.meta.cpu().numpy()
+        V = int(meta[_lib.META_V])
+        present = [int(c) for c in meta[_lib.META_CLS_OF_SLOT:_lib.META_CLS_OF_SLOT + V]]
+        out = dict(V=V, present=present, num_list=[], n_hard=[], valid_ids=[], hard_ids=[])
+        for c in present:
+            nv, nh = int(meta[_lib.META_N_VALID + c]), int(meta[_lib.META_N_HARD + c])
+            out["num_list"].append(nv)
+            out["n_hard"].append(nh)
+            out["valid_ids"].append(ws.valid_list[c * ws.N:c * ws.N + nv].cpu().numpy())
+            out["hard_ids"].append(ws.hard_list[c * ws.N:c * ws.N + nh].cpu().numpy())
+        return out
+
+    def sample_indices(self, seed, offset):
+        """Materialise the draws the scorer would make on the fly for (seed, offset) on the last forward's selection."""
+        ws = self.last["ws"]
+        C = ws.key[1]
+        dev = ws.meta.device
+        a = torch.empty(C, self.num_queries, device=dev, dtype=torch.int32)
+        n = torch.empty(C, self.num_queries, self.num_negatives, device=dev, dtype=torch.int32)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            check(lib.css_sample(ptr(ws.meta), ptr(ws.class_cdf), int(seed), int(offset), C, self.num_queries,
+                                 self.num_negatives, ptr(a), ptr(n), stream_ptr()), "css_sample")
+        return a, n

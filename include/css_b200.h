@@ -1,0 +1,172 @@
+/*
+ * css_b200.h -- C ABI of libcss_b200.so: the B200 (sm_100a) representation-space hot path of CSS.
+ *
+ * Drop-in boundary.  The reference (WangChangqi98/CSS) is pure Python/PyTorch and has no FFI of its own;
+ * every entry point below therefore replaces a block of eager PyTorch statements, cited as
+ * <file>:<lines> relative to the reference root.  The Python bindings a maintainer adds on the
+ * reference side are shown in INTEGRATION.md (ctypes, `css_b200/_lib.py`).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; tensors are contiguous, NCHW;
+ *   - the caller owns every buffer (inputs, outputs, scratch); the library never allocates or frees
+ *     device memory and keeps no global device state;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation, and is CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = argument error (see CSS_E_*), >0 = cudaError_t of the failed launch;
+ *     `css_last_error()` returns a thread-local message for the last non-zero return;
+ *   - D (feature width) must be 256: the reference hard-codes output_dim=256 (mix_label.py:75,93);
+ *     C (classes) must be in [1, 32] (per-pixel class sets are 32-bit masks).
+ *
+ * Pixel ids: pixel (b, y, x) of a [B, *, h, w] map has id (b*h + y)*w + x, the row-major order in which the
+ * reference's boolean-mask gathers enumerate pixels (loss.py:111-112).
+ */
+#ifndef CSS_B200_H
+#define CSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSS_B200_VERSION 100
+
+#define CSS_E_ARG      (-1)   /* null pointer / non-positive size                     */
+#define CSS_E_DIM      (-2)   /* D != 256 or C outside [1,32]                          */
+#define CSS_E_DTYPE    (-3)   /* unsupported rep dtype                                 */
+#define CSS_E_SIZE     (-4)   /* problem exceeds an int32 index range                  */
+
+#define CSS_DTYPE_F32  0
+#define CSS_DTYPE_BF16 1
+
+#define CSS_SIM_COS      0    /* cosine similarities                                   */
+#define CSS_SIM_SOFTMAX  1    /* softmax_c(cos / temp)                                 */
+
+#define CSS_FUSE_NONE    0    /* cross / ori strategies: no fused label                */
+#define CSS_FUSE_MIX     1    /* mix strategy: agree ? label_cls : 255                 */
+
+/* number of int32 words in the selection meta block (see css_select) */
+#define CSS_META_WORDS   256
+/* offsets (int32 words) into meta */
+#define CSS_META_V            0      /* number of locally present classes                        */
+#define CSS_META_N_VALID      32     /* [32] valid-pixel count per class                          */
+#define CSS_META_N_HARD       64     /* [32] hard-pixel count per class                           */
+#define CSS_META_CLS_OF_SLOT  96     /* [32] class id of the k-th present class (increasing)      */
+#define CSS_META_SLOT_OF_CLS  128    /* [32] slot of a class, -1 when absent                      */
+
+int         css_version(void);
+const char* css_last_error(void);
+/* number of streaming multiprocessors of the current device (grid sizing); <0 on error */
+int         css_sm_count(void);
+/* cumulative number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long css_launch_count(void);
+
+/* ---- stage 1 / 1b --------------------------------------------------------------------------------------------
+ * Cosine (mode CSS_SIM_COS) or softmax (CSS_SIM_SOFTMAX) similarity of every pixel's D-vector against the class
+ * prototypes.  Replaces ddp_model.py:104-110 (teacher sim_mat), :147-154 / :230-237 (student prob_all).
+ *   rep        [B, D, h, w]  rep_dtype            prototypes [C, D] f32
+ *   proto_scratch  f32[D * 32]  scratch (normalised, transposed prototypes; F.normalize eps 1e-12)
+ *   out        [B, C, h, w] f32
+ */
+int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
+                int B, int C, int D, int h, int w, int mode, float temp, float* out, void* stream);
+
+/* ---- stage 1 / 1' / 2 ----------------------------------------------------------------------------------------
+ * Fused bilinear (align_corners=True) up-sampling + softmax + max of the similarity map and of the class logits,
+ * plus the mix-label fusion, at crop resolution; the [B,C,H,W] up-sampled tensors are never materialised.
+ * Replaces ddp_model.py:111-118 (Model_mix), :196-199 (Model_cross), :36-37 (Model_ori_pseudo).
+ *   sim     [B,C,h,w] f32 or NULL (then the *_rep outputs and `fused` must be NULL)
+ *   logits  [B,C,h,w] f32 or NULL (then the *_cls outputs and `fused` must be NULL)
+ *   conf_*  [B,H,W] f32, label_* [B,H,W] i64, fused [B,H,W] f32 in {0..C-1, 255}; any output may be NULL.
+ */
+int css_upsample_label_fuse(const float* sim, const float* logits, float temp, int fuse_mode,
+                            int B, int C, int h, int w, int H, int W,
+                            float* conf_rep, int64_t* label_rep, float* conf_cls, int64_t* label_cls,
+                            float* fused, void* stream);
+
+/* ---- stage 3: selection ----------------------------------------------------------------------------------------
+ * valid[p,c] = label[p,c]*mask[p] != 0, hard[p,c] = valid && prob[p,c] < strong_threshold, and the ORDER-PRESERVING
+ * (row-major) per-class compaction of both.  Replaces loss.py:80,94-99,111-113.
+ *   label [B2,C,h,w] f32, mask [B2,1,h,w] f32, prob [B2,C,h,w] f32          N = B2*h*w
+ *   valid_bits, hard_bits   u32[N]      per-pixel class sets
+ *   tile_counts             i32[2*C*T]  scratch, T = css_select_tiles(N)
+ *   valid_list, hard_list   i32[C*N]    class c's pixel ids start at c*N (fixed stride, no cross-class scan)
+ *   meta                    i32[CSS_META_WORDS]   counts / present classes, layout CSS_META_*
+ */
+int css_select_tiles(int N);
+int css_select(const float* label, const float* mask, const float* prob, float strong_threshold,
+               int B2, int C, int h, int w,
+               uint32_t* valid_bits, uint32_t* hard_bits, int32_t* tile_counts,
+               int32_t* valid_list, int32_t* hard_list, int32_t* meta, void* stream);
+
+/* ---- stage 4a: one streaming read of rep -------------------------------------------------------------------------
+ * Per-class feature sums and counts of this rank (the all-reduce payload that replaces the reference's all_gather,
+ * loss.py:77,81,102) and the pixel-major normalised copy the scoring kernel gathers from.
+ *   rep [B2,D,h,w] rep_dtype, valid_bits u32[N], meta i32[CSS_META_WORDS] (from css_select: the local counts)
+ *   rows_hat  f32[N*D]   x_p / max(||x_p||, 1e-8), pixel-major (row p = pixel id p)
+ *   norms     f32[N]     ||x_p||
+ *   partials  f32[css_stream_blocks() * (C*D)] + touched u32[css_stream_blocks()]  scratch (deterministic reduce)
+ *   class_stats f32[C*(D+1)]  row c = [sum_d ... , count]
+ */
+int css_stream_blocks(void);
+int css_stream_rep(const void* rep, int rep_dtype, const uint32_t* valid_bits, const int32_t* meta,
+                   int B2, int C, int D, int h, int w,
+                   float* rows_hat, float* norms, float* partials, uint32_t* touched, float* class_stats,
+                   void* stream);
+
+/* ---- stage 4b: prototype EMA --------------------------------------------------------------------------------------
+ * For every class present on THIS rank: mean = global_sum / global_count; prototypes[c] = mean if sum(prototypes[c])==0
+ * else alpha*prototypes[c] + one_minus_alpha*mean, in place.  Replaces loss.py:101-109.  (one_minus_alpha is passed
+ * separately because the reference evaluates 1 - alpha in double before rounding to fp32.)  Also emits what scoring needs:
+ *   proto_hat f32[C*D]   updated prototypes / max(norm, 1e-8)
+ *   class_cdf f32[32*32] row k: inclusive CDF of softmax(cos(P_k, P_j)/temp) over the other present classes in the
+ *                        rotated order k+1..V-1,0..k-1 (loss.py:133-135)
+ *   class_stats is the (all-reduced) [C, D+1] block; meta supplies the LOCAL counts.
+ */
+int css_proto_ema(float* prototypes, const float* class_stats, const int32_t* meta, float alpha,
+                  float one_minus_alpha, float temp, int C, int D, float* proto_hat, float* class_cdf, void* stream);
+
+/* ---- stage 3: sampling (materialised; the scoring kernel can also draw on the fly) ---------------------------------
+ * Anchors: Q uniform indices into each present class's hard list (loss.py:127).  Negatives: Nn iid draws of
+ * (class ~ Categorical(class_cdf[k]), index ~ Uniform within that class's valid list), expressed as indices into the
+ * rotated concatenation of valid lists (loss.py:136-142).  Philox4x32-10 keyed by (seed, offset); no host sync.
+ *   anchor_idx i32[C*Q], neg_idx i32[C*Q*Nn]  (slot-major; slots >= V and slots without hard pixels are left at -1)
+ */
+int css_sample(const int32_t* meta, const float* class_cdf, uint64_t seed, uint64_t offset, int C, int Q, int Nn,
+               int32_t* anchor_idx, int32_t* neg_idx, void* stream);
+
+/* ---- stage 3: scoring + cross-entropy + d loss / d anchor ------------------------------------------------------------
+ * Replaces loss.py:124-149 and its autograd backward up to the anchor rows.
+ *   anchor_idx / neg_idx: as produced by css_sample or recorded from the reference; NULL = draw on the fly with
+ *   (seed, offset), bit-identical to css_sample with the same arguments.
+ *   loss_kq f32[C*Q], anchor_px i32[C*Q] (pixel id of each anchor, -1 if none), grad_anchor f32[C*Q*D] or NULL,
+ *   loss f32[1] = (1/V) sum_k (1/Q) sum_q loss_kq, exactly 0 when V <= 1.
+ */
+int css_score_ce(const float* rows_hat, const float* norms, const float* proto_hat, const float* class_cdf,
+                 const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta,
+                 const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset,
+                 int N, int C, int D, int Q, int Nn, float temp,
+                 float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream);
+
+/* ---- backward: dense grad_rep ------------------------------------------------------------------------------------------
+ * grad_rep [B2,D,h,w] f32 = 0, then += (*grad_out) * grad_anchor[kq] at every anchor pixel (duplicates accumulate).
+ * Replaces the autograd index_put / zeros_like chain of loss.py:111-112,128.
+ */
+int css_grad_scatter(const float* grad_out, const int32_t* anchor_px, const float* grad_anchor,
+                     int n_anchor, int B2, int D, int h, int w, float* grad_rep, void* stream);
+
+/* ---- stage 2 glue fast path -----------------------------------------------------------------------------
+ * Fused weak-threshold mask + one-hot + nearest down-sampling: emits label_all / mask_all at rep resolution directly
+ * from the crop-resolution label maps.  Replaces mix_label.py:175-183 (mode 1: label_onehot_2 for the unlabelled half),
+ * cross_label.py:178-185 and ori_pseudo.py:171-178 (mode 0).
+ *   label_l [B,H,W] i64, label_u [B,H,W] i64, conf_u [B,H,W] f32 -> label_all [2B,C,h,w] f32, mask_all [2B,1,h,w] f32
+ */
+int css_threshold_glue(const int64_t* label_l, const int64_t* label_u, const float* conf_u, float weak_threshold,
+                       int mode, int B, int C, int H, int W, int h, int w,
+                       float* label_all, float* mask_all, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSS_B200_H */

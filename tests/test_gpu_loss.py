@@ -1,0 +1,300 @@
+"""GPU parity of Contrast_Loss (selection, class statistics, prototype EMA, sampling, scoring + CE, backward) through the
+C ABI, against the golden bundles recorded from the live reference (its own RNG draws fed back) and against the numpy
+oracle on larger seeded inputs.  Selection lists / counts / index->pixel mapping: exactly equal.  Loss, gradient,
+prototypes: rel 1e-4 (BASELINE.json north_star fp32 tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import css_oracle as O
+from tests.helpers import load_golden, recorded, slot_major
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+LOSS_CASES = ["loss_ori_c5", "loss_mix_c21", "loss_nohard_c7", "loss_single_c4", "loss_cross_c19"]
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def scored_slots(sel):
+    return [k for k in range(sel["V"]) if sel["n_hard"][k] > 0] if sel["V"] > 1 else []
+
+
+def run_gpu(crit, rep, label, mask, prob, protos, indices=None):
+    rep_t = dev(rep).requires_grad_(True)
+    loss = crit(rep_t, dev(label), dev(mask), dev(prob), protos, _indices=indices)
+    loss.backward()
+    return loss, rep_t.grad
+
+
+def check_selection(sel, info):
+    assert sel["V"] == info["V"] and sel["present"] == info["present"] and sel["num_list"] == info["num_list"]
+    for k in range(sel["V"]):
+        assert np.array_equal(sel["valid_ids"][k], info["valid_ids"][k]), f"valid list of slot {k}"
+        assert np.array_equal(sel["hard_ids"][k], info["hard_ids"][k]), f"hard list of slot {k}"
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_contrast_loss_against_reference_golden(name):
+    """Reference's recorded indices fed to the CUDA path: loss / grad / prototypes vs the reference's own outputs."""
+    import css_b200
+    g = load_golden(name)
+    C, Q, Nn = int(g["C"]), int(g["Q"]), int(g["Nn"])
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=float(g["temp"]), strong_threshold=float(g["strong"]), alpha=float(g["alpha"]))
+    crit = css_b200.Contrast_Loss(**kw).cuda()
+    for s in range(int(g["steps"])):
+        rep, label, mask, prob = g[f"s{s}_rep"], g[f"s{s}_label"].astype(np.float32), g[f"s{s}_mask"].astype(np.float32), g[f"s{s}_prob"]
+        a_rec, n_rec = recorded(g, s)
+        # selection does not depend on the draws: run once without gradient to learn the scored slots
+        protos = dev(g[f"s{s}_proto_in"])
+        with torch.no_grad():
+            crit(dev(rep), dev(label), dev(mask), dev(prob), protos.clone())
+        sel = crit.selection()
+        p_or = g[f"s{s}_proto_in"].copy()
+        l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=O.RecordedDraws(a_rec, n_rec), **kw)
+        check_selection(sel, info)
+        slots = scored_slots(sel)
+        assert slots == info["scored"] and len(slots) == int(g[f"s{s}_n_scored"])
+        a, n = slot_major(a_rec, n_rec, slots, C, Q, Nn)
+        loss, grad = run_gpu(crit, rep, label, mask, prob, protos, (dev(a), dev(n)))
+        assert loss.dim() == 0 and loss.dtype == torch.float32
+        np.testing.assert_allclose(protos.cpu().numpy(), g[f"s{s}_proto_out"], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(loss.item(), g[f"s{s}_loss"], rtol=RTOL, atol=1e-6)
+        gref = g[f"s{s}_grad"]
+        gg = grad.cpu().numpy()
+        assert np.array_equal(gg != 0, gref != 0), "gradient support differs from the reference"
+        np.testing.assert_allclose(gg, gref, rtol=RTOL, atol=1e-7)
+        # anchor pixels are exactly the reference's
+        apx = crit.last["anchor_px"].cpu().numpy().reshape(C, Q)
+        for k, px in zip(info["scored"], info["anchor_pixels"]):
+            assert np.array_equal(apx[k], px)
+        if len(slots) == 0:
+            assert loss.item() == 0.0 and not gg.any()
+
+
+@pytest.mark.parametrize("B2,C,h,w,Q,Nn,strategy,strong", [(2, 21, 81, 81, 256, 512, "ori", 0.97),     # BASELINE config 1
+                                                           (2, 19, 33, 47, 64, 100, "mix", 0.5),
+                                                           (3, 32, 20, 20, 7, 3, "ori", 0.9)])
+def test_contrast_loss_against_oracle_device_draws(B2, C, h, w, Q, Nn, strategy, strong):
+    """Draws come from the device sampler (css_sample), are fed to the oracle, and the on-the-fly path must reproduce the
+    fed path bit for bit."""
+    import css_b200
+    from css_b200 import synth
+    d = synth.student_batch(B2, C, h, w, seed=77 + C, strategy=strategy, block=8 if h > 40 else 3)
+    protos0 = synth.warm_prototypes(C, seed=5, zero_rows=(1,))
+    if strategy == "mix":
+        d["prob"] = torch.from_numpy(O.proto_softmax_sim(d["rep"].numpy(), protos0.numpy(), 0.5))
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=strong, alpha=0.99)
+    crit = css_b200.Contrast_Loss(seed=1234, **kw).cuda()
+    rep, label, mask, prob = (d[k].numpy() for k in ("rep", "label", "mask", "prob"))
+    protos = protos0.clone().cuda()
+    loss_fly, grad_fly = run_gpu(crit, rep, label, mask, prob, protos)          # on-the-fly draws, offset 0
+    sel = crit.selection()
+    a, n = crit.sample_indices(1234, 0)
+    slots = scored_slots(sel)
+    a_np, n_np = a.cpu().numpy(), n.cpu().numpy()
+    for k in range(C):
+        if k in slots:
+            assert a_np[k].min() >= 0 and a_np[k].max() < sel["n_hard"][k]
+            tot = sum(sel["num_list"]) - sel["num_list"][k]
+            assert n_np[k].min() >= 0 and n_np[k].max() < tot
+        else:
+            assert (a_np[k] == -1).all() and (n_np[k] == -1).all()
+    p_or = protos0.numpy().copy()
+    sampler = O.RecordedDraws([a_np[k] for k in slots], [n_np[k].reshape(-1) for k in slots])
+    l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=sampler, **kw)
+    check_selection(sel, info)
+    assert info["scored"] == slots
+    np.testing.assert_allclose(protos.cpu().numpy(), p_or, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(loss_fly.item(), l_or, rtol=RTOL)
+    gg = grad_fly.cpu().numpy()
+    assert np.array_equal(gg != 0, g_or != 0)
+    np.testing.assert_allclose(gg, g_or, rtol=RTOL, atol=1e-7)
+    # fed path == on-the-fly path, bit for bit (loss) and to rounding of the atomic accumulation order (grad)
+    protos2 = protos0.clone().cuda()
+    loss_fed, grad_fed = run_gpu(crit, rep, label, mask, prob, protos2, (a, n))
+    assert loss_fed.item() == loss_fly.item()
+    assert torch.equal(protos2, protos)
+    torch.testing.assert_close(grad_fed, grad_fly, rtol=1e-6, atol=1e-9)
+    # a different offset gives different draws
+    a2, _ = crit.sample_indices(1234, 1)
+    assert not torch.equal(a2, a)
+
+
+def test_multi_hot_labels_and_empty_batch():
+    """label need not be one-hot for the reference (a pixel may be valid for several classes); an all-masked batch
+    gives V = 0, loss exactly 0, dense zero gradient, prototypes untouched."""
+    import css_b200
+    g = torch.Generator().manual_seed(3)
+    B2, C, h, w, Q, Nn = 2, 6, 12, 10, 8, 16
+    rep = torch.randn(B2, 256, h, w, generator=g).numpy()
+    label = (torch.rand(B2, C, h, w, generator=g) < 0.3).float().numpy()
+    mask = (torch.rand(B2, 1, h, w, generator=g) < 0.7).float().numpy()
+    prob = torch.rand(B2, C, h, w, generator=g).numpy()
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.6, alpha=0.99)
+    crit = css_b200.Contrast_Loss(seed=7, **kw).cuda()
+    protos = torch.zeros(C, 256).cuda()
+    loss, grad = run_gpu(crit, rep, label, mask, prob, protos)
+    sel = crit.selection()
+    a, n = crit.sample_indices(7, 0)
+    slots = scored_slots(sel)
+    p_or = np.zeros((C, 256), np.float32)
+    sampler = O.RecordedDraws([a.cpu().numpy()[k] for k in slots], [n.cpu().numpy()[k].reshape(-1) for k in slots])
+    l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=sampler, **kw)
+    check_selection(sel, info)
+    np.testing.assert_allclose(loss.item(), l_or, rtol=RTOL)
+    np.testing.assert_allclose(grad.cpu().numpy(), g_or, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(protos.cpu().numpy(), p_or, rtol=RTOL, atol=1e-6)
+    # empty
+    protos = torch.ones(C, 256).cuda()
+    loss, grad = run_gpu(crit, rep, label, np.zeros_like(mask), prob, protos)
+    assert loss.item() == 0.0 and not grad.any().item() and grad.shape == (B2, 256, h, w)
+    assert crit.selection()["V"] == 0 and torch.equal(protos, torch.ones(C, 256).cuda())
+
+
+def test_sampler_distributions():
+    """chi-square tests of the device Philox sampler: anchor uniformity, class histogram vs
+    softmax(cos(P_k,P_j)/temp), uniformity inside a class."""
+    import css_b200
+    from css_b200 import synth
+    from scipy import stats
+    B2, C, h, w, Q, Nn = 2, 5, 16, 16, 512, 256
+    d = synth.student_batch(B2, C, h, w, seed=11, block=4)
+    crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.97, seed=99).cuda()
+    protos = synth.warm_prototypes(C, seed=2).cuda()
+    with torch.no_grad():
+        crit(d["rep"].cuda(), d["label"].cuda(), d["mask"].cuda(), d["prob"].cuda(), protos)
+    sel = crit.selection()
+    assert sel["V"] == C
+    a, n = crit.sample_indices(99, 0)
+    a, n = a.cpu().numpy(), n.cpu().numpy()
+    proto_rep = protos.cpu().numpy()
+    for k in range(C):
+        if sel["n_hard"][k] == 0:
+            continue
+        # (a) anchors uniform over the hard list (coarse bins so that expected counts are large)
+        bins = min(8, sel["n_hard"][k])
+        cnt = np.bincount((a[k].astype(np.int64) * bins) // sel["n_hard"][k], minlength=bins)
+        assert stats.chisquare(cnt).pvalue > 1e-4
+        # (b) class histogram of the negatives vs proto_prob
+        others = sel["num_list"][k + 1:] + sel["num_list"][:k]
+        edges = np.concatenate([[0], np.cumsum(others)])
+        seg = np.searchsorted(edges, n[k].reshape(-1), side="right") - 1
+        obs = np.bincount(seg, minlength=C - 1)
+        p = O.proto_class_prob(proto_rep[sel["present"]], k, 0.5).astype(np.float64)
+        assert stats.chisquare(obs, p / p.sum() * obs.sum()).pvalue > 1e-4
+        # (c) uniform inside the largest segment
+        j = int(np.argmax(others))
+        inside = n[k].reshape(-1)[seg == j] - edges[j]
+        bins = min(8, others[j])
+        cnt = np.bincount((inside.astype(np.int64) * bins) // others[j], minlength=bins)
+        assert stats.chisquare(cnt).pvalue > 1e-4
+
+
+def test_full_size_properties_voc_batch():
+    """BASELINE config 2 shape (B2=16, C=21, 81x81, Q=256, Nn=512): size-independent properties instead of the oracle."""
+    import css_b200
+    from css_b200 import synth
+    B2, C, h, w, Q, Nn = 16, 21, 81, 81, 256, 512
+    d = synth.student_batch(B2, C, h, w, seed=3407)
+    crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.97, seed=5).cuda()
+    rep = d["rep"].cuda().requires_grad_(True)
+    label, mask, prob = d["label"].cuda(), d["mask"].cuda(), d["prob"].cuda()
+    protos = torch.zeros(C, 256).cuda()
+    loss = crit(rep, label, mask, prob, protos)
+    loss.backward()
+    sel = crit.selection()
+    valid = (label * mask) != 0
+    # counts / sortedness / membership of the compaction
+    assert sel["num_list"] == [int(valid[:, c].sum()) for c in sel["present"]]
+    for k, c in enumerate(sel["present"]):
+        ids = sel["valid_ids"][k]
+        assert np.all(np.diff(ids) > 0)
+        assert np.array_equal(ids, torch.nonzero(valid[:, c].reshape(-1)).reshape(-1).cpu().numpy())
+        hard = valid[:, c] & (prob[:, c] < 0.97)
+        assert np.array_equal(sel["hard_ids"][k], torch.nonzero(hard.reshape(-1)).reshape(-1).cpu().numpy())
+    # first-touch prototypes are the class means of the raw features
+    x = d["rep"].permute(0, 2, 3, 1).reshape(-1, 256)
+    for k, c in enumerate(sel["present"]):
+        np.testing.assert_allclose(protos[c].cpu().numpy(), x[sel["valid_ids"][k]].double().mean(0).numpy(), rtol=1e-4, atol=1e-5)
+    # gradient support == anchor pixels; loss positive and below log(1+Nn) + 2/temp
+    apx = crit.last["anchor_px"].cpu().numpy()
+    apx = np.unique(apx[apx >= 0])
+    gpix = torch.nonzero(rep.grad.abs().sum(1).reshape(-1)).reshape(-1).cpu().numpy()
+    assert set(gpix).issubset(set(apx)) and len(gpix) > 0.9 * len(apx)
+    assert 0 < loss.item() < np.log(1 + Nn) + 4
+    # cosine scoring is invariant to a positive rescaling of rep; prototypes (raw means) scale linearly
+    crit2 = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.97, seed=5).cuda()
+    protos2 = torch.zeros(C, 256).cuda()
+    loss2 = crit2((d["rep"] * 4).cuda(), label, mask, prob, protos2)
+    np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-5)
+    torch.testing.assert_close(protos2, protos * 4, rtol=1e-5, atol=1e-6)
+    # same seed/offset -> same loss bit for bit (deterministic reductions everywhere on the forward path)
+    crit3 = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.97, seed=5).cuda()
+    protos3 = torch.zeros(C, 256).cuda()
+    assert crit3(d["rep"].cuda(), label, mask, prob, protos3).item() == loss.item()
+    assert torch.equal(protos3, protos)
+    # EMA branch on a second step: p <- alpha p + (1-alpha) mean
+    before = protos.clone()
+    crit(d["rep"].cuda(), label, mask, prob, protos)
+    torch.testing.assert_close(protos, 0.99 * before + (1 - 0.99) * before, rtol=1e-5, atol=1e-6)
+
+
+def test_model_shells_with_stub_network():
+    """Model_mix / Model_cross / Model_ori_pseudo shells (stub network, pass-through aug) reproduce the reference tuples
+    recorded in the stage-1/2 golden bundles."""
+    import css_b200
+    from css_b200 import models
+    from tests.helpers import top2_margin
+
+    class Stub(torch.nn.Module):
+        def __init__(self, outs):
+            super().__init__()
+            self.outs, self.i = outs, 0
+
+        def forward(self, x):
+            o = self.outs[self.i % len(self.outs)]
+            self.i += 1
+            return o
+
+    saved = dict(vars(models.hooks))
+    try:
+        models.hooks.network_factory = lambda enc, **kw: torch.nn.Conv2d(1, 1, 1)
+        models.hooks.batch_transform = lambda a, b, c, **k: (a, b, c)
+        models.hooks.batch_transform_2 = lambda a, b, c, d, **k: (a, b, c, d)
+        models.hooks.batch_transform_3 = lambda a, b, c, d, e, **k: (a, b, c, d, e)
+        models.hooks.generate_cut_gather = lambda a, b, c, mode=None: (a, b, c)
+        models.hooks.generate_cut_gather_2 = lambda a, b, c, d, mode=None: (a, b, c, d)
+        models.hooks.generate_cut_gather_3 = lambda a, b, c, d, e, mode=None: (a, b, c, d, e)
+        for name, cls in (("stage12_mix_c21", models.Model_mix), ("stage12_cross_c19", models.Model_cross)):
+            g = load_golden(name)
+            B, C, H, W, temp = int(g["B"]), int(g["C"]), int(g["H"]), int(g["W"]), float(g["temp"])
+            cfg = {"Dataset": {"crop_size": (H, W), "scale_size": (1.0, 1.0), "mix_mode": "none"}}
+            m = cls(None, num_classes=C, output_dim=256, config=cfg, temp=temp).cuda()
+            rep_all, pred_all = dev(g["rep_all"]), dev(g["pred_all"])
+            m.ema_model = Stub([(dev(g["pred_u"]), dev(g["rep_u"]))])
+            m.model = Stub([(pred_all[:B], rep_all[:B]), (pred_all[B:], rep_all[B:])])
+            img = torch.zeros(B, 3, H, W).cuda()
+            r = m(img, img, dev(g["prototypes"]))
+            assert len(r) == (7 if cls is models.Model_mix else 8)
+            np.testing.assert_allclose(r[-1].cpu().numpy(), g["prob_all"], atol=1e-6)
+            assert torch.equal(r[-2], rep_all)
+            assert r[0].shape == (B, C, H, W) and r[1].shape == (B, C, H, W)
+            if cls is models.Model_mix:
+                assert r[2].dtype == torch.float32
+                np.testing.assert_allclose(r[3].cpu().numpy(), g["conf_cls"], atol=2e-6)
+                np.testing.assert_allclose(r[4].cpu().numpy(), g["conf_rep"], atol=2e-6)
+                assert (r[2].cpu().numpy() != g["fused"]).mean() < 1e-3
+            else:
+                assert r[2].dtype == torch.int64 and r[3].dtype == torch.int64
+                assert (r[2].cpu().numpy() != g["label_cls"]).mean() < 1e-3
+                assert (r[3].cpu().numpy() != g["label_rep"]).mean() < 1e-3
+        m.step = 0
+        m.ema_update()
+        assert m.step == 1
+    finally:
+        for k, v in saved.items():
+            setattr(models.hooks, k, v)
