@@ -60,22 +60,26 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(int32_t* __restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < 2 * C; r += 32) {
         int32_t* row = tile_counts + (size_t)r * T;
-        int running = 0;
-        for (int base = 0; base < T; base += 32) {
-            const int i = base + lane;
-            const int v = (i < T) ? row[i] : 0;
-            int inc = v;
+        const int len = (T + 31) / 32;
+        const int b0 = min(lane * len, T), b1 = min(b0 + len, T);
+        int tot = 0;
+        for (int i = b0; i < b1; ++i) tot += row[i];
+        int inc = tot;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += n;
-            }
-            if (i < T) row[i] = running + inc - v;
-            running += __shfl_sync(0xffffffffu, inc, 31);
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
         }
+        int run = inc - tot;
+        for (int i = b0; i < b1; ++i) {
+            const int v = row[i];
+            row[i] = run;
+            run += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
         if (lane == 0) {
             const int kind = r / C, c = r - kind * C;
-            meta[(kind ? CSS_META_N_HARD : CSS_META_N_VALID) + c] = running;
+            meta[(kind ? CSS_META_N_HARD : CSS_META_N_VALID) + c] = total;
         }
     }
     __syncthreads();

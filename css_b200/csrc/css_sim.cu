@@ -7,97 +7,126 @@
 // prototype preparation: F.normalize(prototypes, dim=-1) (eps 1e-12, ddp_model.py:107), transposed to [D][32]
 // (class-minor, zero padded) so the streaming kernel reads 4 classes per 128-bit shared-memory load.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) proto_prep_kernel(const float* __restrict__ protos, float* __restrict__ scratch, int C) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ float nrm[CSS_CMAX];
-    for (int c = warp; c < CSS_CMAX; c += 8) {
-        float s = 0.f;
-        if (c < C)
-            for (int d = lane; d < CSS_D; d += 32) {
-                float v = protos[c * CSS_D + d];
-                s = fmaf(v, v, s);
-            }
-        s = warp_sum(s);
-        if (lane == 0) nrm[c] = (c < C) ? fmaxf(sqrtf(s), 1e-12f) : 1.f;
+__global__ void __launch_bounds__(CSS_D) proto_prep_kernel(const float* __restrict__ protos, float* __restrict__ scratch, int C) {
+    __shared__ float part[CSS_D / 32];
+    const int c = blockIdx.x, d = threadIdx.x;
+    if (c >= C) {                                   // padding columns
+        scratch[d * CSS_CMAX + c] = 0.f;
+        return;
     }
+    const float v = protos[c * CSS_D + d];
+    const float s = warp_sum(v * v);
+    if ((d & 31) == 0) part[d >> 5] = s;
     __syncthreads();
-    const int d = threadIdx.x;
-    for (int c = 0; c < CSS_CMAX; ++c)
-        scratch[d * CSS_CMAX + c] = (c < C) ? __fdiv_rn(protos[c * CSS_D + d], nrm[c]) : 0.f;
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CSS_D / 32; ++i) n2 += part[i];
+    scratch[d * CSS_CMAX + c] = __fdiv_rn(v, fmaxf(sqrtf(n2), 1e-12f));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: one thread per pixel streams its 256 channels straight from the NCHW map (a warp reads 128 contiguous bytes
-// per channel), keeps 4*NG class dots + the squared norm in registers, prototypes broadcast from shared memory.
+// K1: each thread streams the 256 channels of SM_PPT pixels straight from the NCHW map (a warp reads 128 contiguous
+// bytes per channel and pixel group), keeps SM_PPT x 4*NG class dots + the squared norms in registers, and reads the
+// pre-normalised prototypes as 128-bit shared-memory broadcasts that each feed SM_PPT x 4 FMAs (the register blocking
+// over pixels is what keeps the shared-memory pipe off the critical path).  Persistent CTAs loop over 256-pixel chunks.
 //   cos_c = (x . p_hat_c) / max(||x||, 1e-12)                                   (ddp_model.py:105-109)
 //   mode CSS_SIM_SOFTMAX: softmax_c(cos_c / temp)                               (ddp_model.py:154)
 // Algorithmic bytes / pixel: D*4 read + C*4 written.
 // ---------------------------------------------------------------------------------------------------------------
+#define SM_THREADS 64
+#define SM_PPT 4
+#define SM_CHUNK (SM_THREADS * SM_PPT)
+
 template <int NG>
-__global__ void __launch_bounds__(128) sim_map_kernel(const float* __restrict__ rep, const float* __restrict__ scratch,
-                                                      int hw, int N, int C, int mode, float temp, float* __restrict__ out) {
+__global__ void __launch_bounds__(SM_THREADS) sim_map_kernel(const float* __restrict__ rep, const float* __restrict__ scratch,
+                                                             int hw, int N, int C, int mode, float temp, float* __restrict__ out) {
     __shared__ float4 sp[CSS_D * NG];
-    for (int i = threadIdx.x; i < CSS_D * NG; i += 128) {
+    for (int i = threadIdx.x; i < CSS_D * NG; i += SM_THREADS) {
         int d = i / NG, g = i - d * NG;
         sp[i] = reinterpret_cast<const float4*>(scratch)[d * (CSS_CMAX / 4) + g];
     }
     __syncthreads();
-    const int p = blockIdx.x * 128 + threadIdx.x;
-    if (p >= N) return;
-    const int b = p / hw, s = p - b * hw;
-    const float* x = rep + (size_t)b * CSS_D * hw + s;
-
-    float acc[4 * NG];
+    const int n_chunks = (N + SM_CHUNK - 1) / SM_CHUNK;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const float* x[SM_PPT];
+        int pix[SM_PPT];
 #pragma unroll
-    for (int i = 0; i < 4 * NG; ++i) acc[i] = 0.f;
-    float n2 = 0.f;
-    constexpr int U = 8;
-    for (int d0 = 0; d0 < CSS_D; d0 += U) {
-        float v[U];
+        for (int j = 0; j < SM_PPT; ++j) {
+            pix[j] = chunk * SM_CHUNK + j * SM_THREADS + threadIdx.x;
+            const int p = min(pix[j], N - 1);                    // out-of-range lanes re-read the last pixel, never write
+            const int b = p / hw;
+            x[j] = rep + (size_t)b * CSS_D * hw + (p - b * hw);
+        }
+        float acc[SM_PPT][4 * NG];
+        float n2[SM_PPT];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ldg_stream(x + (size_t)(d0 + u) * hw);
+        for (int j = 0; j < SM_PPT; ++j) {
+            n2[j] = 0.f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            n2 = fmaf(v[u], v[u], n2);
+            for (int i = 0; i < 4 * NG; ++i) acc[j][i] = 0.f;
+        }
+        constexpr int U = 8;
+#pragma unroll 1
+        for (int d0 = 0; d0 < CSS_D; d0 += U) {
+            float v[U][SM_PPT];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                float4 q = sp[(d0 + u) * NG + g];
-                acc[4 * g + 0] = fmaf(v[u], q.x, acc[4 * g + 0]);
-                acc[4 * g + 1] = fmaf(v[u], q.y, acc[4 * g + 1]);
-                acc[4 * g + 2] = fmaf(v[u], q.z, acc[4 * g + 2]);
-                acc[4 * g + 3] = fmaf(v[u], q.w, acc[4 * g + 3]);
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < SM_PPT; ++j) v[u][j] = ldg_stream(x[j] + (size_t)(d0 + u) * hw);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int j = 0; j < SM_PPT; ++j) n2[j] = fmaf(v[u][j], v[u][j], n2[j]);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const float4 q = sp[(d0 + u) * NG + g];
+#pragma unroll
+                    for (int j = 0; j < SM_PPT; ++j) {
+                        acc[j][4 * g + 0] = fmaf(v[u][j], q.x, acc[j][4 * g + 0]);
+                        acc[j][4 * g + 1] = fmaf(v[u][j], q.y, acc[j][4 * g + 1]);
+                        acc[j][4 * g + 2] = fmaf(v[u][j], q.z, acc[j][4 * g + 2]);
+                        acc[j][4 * g + 3] = fmaf(v[u][j], q.w, acc[j][4 * g + 3]);
+                    }
+                }
             }
         }
-    }
-    const float nrm = fmaxf(sqrtf(n2), 1e-12f);
-    float* o = out + (size_t)b * C * hw + s;
-    if (mode == CSS_SIM_COS) {
 #pragma unroll
-        for (int c = 0; c < 4 * NG; ++c)
-            if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[c], nrm);
-    } else {
-        float m = -INFINITY;
+        for (int j = 0; j < SM_PPT; ++j) {
+            if (pix[j] >= N) continue;
+            const int b = pix[j] / hw, s = pix[j] - b * hw;
+            const float nrm = fmaxf(sqrtf(n2[j]), 1e-12f);
+            float* o = out + (size_t)b * C * hw + s;
+            if (mode == CSS_SIM_COS) {
 #pragma unroll
-        for (int c = 0; c < 4 * NG; ++c) {
-            acc[c] = __fdiv_rn(__fdiv_rn(acc[c], nrm), temp);
-            if (c < C) m = fmaxf(m, acc[c]);
+                for (int c = 0; c < 4 * NG; ++c)
+                    if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[j][c], nrm);
+            } else {
+                float m = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4 * NG; ++c) {
+                    acc[j][c] = __fdiv_rn(__fdiv_rn(acc[j][c], nrm), temp);
+                    if (c < C) m = fmaxf(m, acc[j][c]);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4 * NG; ++c) {
+                    acc[j][c] = (c < C) ? expf(acc[j][c] - m) : 0.f;
+                    sum += acc[j][c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4 * NG; ++c)
+                    if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[j][c], sum);
+            }
         }
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4 * NG; ++c) {
-            acc[c] = (c < C) ? expf(acc[c] - m) : 0.f;
-            sum += acc[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 4 * NG; ++c)
-            if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[c], sum);
     }
 }
 
 template <int NG>
 static void launch_sim(const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
                        cudaStream_t st) {
-    sim_map_kernel<NG><<<(N + 127) / 128, 128, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out);
+    const int n_chunks = (N + SM_CHUNK - 1) / SM_CHUNK;
+    const int grid = n_chunks < css_cached_sm_count() * 8 ? n_chunks : css_cached_sm_count() * 8;
+    sim_map_kernel<NG><<<grid, SM_THREADS, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out);
 }
 
 extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C,
@@ -110,7 +139,7 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
     CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_sim_map: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w, N = B * hw;
-    proto_prep_kernel<<<1, 256, 0, st>>>(prototypes, proto_scratch, C);
+    proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
     const float* r = (const float*)rep;
     switch ((C + 3) / 4) {
         case 1: launch_sim<1>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
@@ -127,29 +156,35 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: one thread per crop pixel.  4-tap align_corners=True bilinear of the C similarities and the C logits read from
-// the rep-resolution maps (L2 resident), softmax(/temp) + max with first-index tie breaking, mix fusion.  Arithmetic
-// follows ATen's upsample_bilinear2d op for op (explicit _rn intrinsics: no FMA contraction):
+// K2: fused bilinear (align_corners=True) up-sampling + softmax + max (+ mix fusion) at crop resolution.
+// A CTA owns an 8 x 32 tile of crop pixels of one image; the few low-resolution pixels that tile touches (for 81 -> 321:
+// 4 x 10 per class) are staged ONCE in shared memory for all C classes of both maps, so the 4-tap reads are shared-memory
+// broadcasts instead of 168 L1/L2 loads per thread.  Arithmetic follows ATen's upsample_bilinear2d op for op (explicit
+// _rn intrinsics: no FMA contraction):
 //   src = ((in-1)/(out-1)) * dst ; i0 = int(src) ; i1 = i0 + (i0 < in-1) ; lam = src - i0
 //   v = (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11)
-// Algorithmic bytes / crop pixel: 28 written (2 x f32 conf, 2 x i64 label, f32 fused); the taps come from L2.
+// Algorithmic bytes / crop pixel: 28 written (2 x f32 conf, 2 x i64 label, f32 fused) + the low-res maps read once.
 // ---------------------------------------------------------------------------------------------------------------
+#define K2_TH 8
+#define K2_TW 32
+
 struct Taps {
     int o00, o01, o10, o11;
     float hx, lx, hy, ly;
 };
 
+// softmax + max over the C up-sampled values of one map; `src` is the staged tile ([C][cstride]) or the global map
 template <bool USE_TEMP>
-__device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ src, int C, int hw, const Taps& t, float temp,
+__device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ src, int C, int cstride, const Taps& t, float temp,
                                                      float& conf, int& label) {
     float v[CSS_CMAX];
     float m = -INFINITY;
 #pragma unroll
     for (int c = 0; c < CSS_CMAX; ++c) {
         if (c < C) {
-            const float* s = src + (size_t)c * hw;
-            float top = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o00)), __fmul_rn(t.lx, __ldg(s + t.o01)));
-            float bot = __fadd_rn(__fmul_rn(t.hx, __ldg(s + t.o10)), __fmul_rn(t.lx, __ldg(s + t.o11)));
+            const float* s = src + c * cstride;
+            float top = __fadd_rn(__fmul_rn(t.hx, s[t.o00]), __fmul_rn(t.lx, s[t.o01]));
+            float bot = __fadd_rn(__fmul_rn(t.hx, s[t.o10]), __fmul_rn(t.lx, s[t.o11]));
             float val = __fadd_rn(__fmul_rn(t.hy, top), __fmul_rn(t.ly, bot));
             if (USE_TEMP) val = __fdiv_rn(val, temp);
             v[c] = val;
@@ -161,7 +196,7 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
 #pragma unroll
     for (int c = 0; c < CSS_CMAX; ++c) {
         if (c < C) {
-            v[c] = expf(v[c] - m);
+            v[c] = __expf(v[c] - m);          // exp(0) == 1 exactly for the arg-max, monotone elsewhere
             sum += v[c];
             emax = fmaxf(emax, v[c]);
         }
@@ -175,15 +210,36 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
     label = lab;
 }
 
-__global__ void __launch_bounds__(128) upsample_label_fuse_kernel(const float* __restrict__ sim, const float* __restrict__ logits,
-                                                                  float temp, int fuse_mode, int C, int h, int w, int H, int W,
-                                                                  float ry, float rx, float* __restrict__ conf_rep,
-                                                                  int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
-                                                                  int64_t* __restrict__ label_cls, float* __restrict__ fused) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (idx >= H * W) return;
-    const int Y = idx / W, X = idx - Y * W;
+template <bool STAGED>
+__global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
+    const float* __restrict__ sim, const float* __restrict__ logits, float temp, int fuse_mode, int C, int h, int w, int H, int W,
+    float ry, float rx, int tile_cap, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
+    int64_t* __restrict__ label_cls, float* __restrict__ fused) {
+    extern __shared__ float tile[];                 // [2 maps][C][in_th * in_tw]  (STAGED only)
+    const int b = blockIdx.z;
+    const int Y0 = blockIdx.y * K2_TH, X0 = blockIdx.x * K2_TW;
+    const int Y = Y0 + (threadIdx.x >> 5), X = X0 + (threadIdx.x & 31);
+    const int hw = h * w;
+    int ys0 = 0, xs0 = 0, in_tw = w, cstride = hw;
+    if (STAGED) {
+        const int Yl = min(Y0 + K2_TH - 1, H - 1), Xl = min(X0 + K2_TW - 1, W - 1);
+        ys0 = (int)__fmul_rn(ry, (float)Y0);
+        xs0 = (int)__fmul_rn(rx, (float)X0);
+        const int ye = (int)__fmul_rn(ry, (float)Yl), xe = (int)__fmul_rn(rx, (float)Xl);
+        const int in_th = min(ye + 1, h - 1) - ys0 + 1;
+        in_tw = min(xe + 1, w - 1) - xs0 + 1;
+        cstride = in_th * in_tw;                    // <= tile_cap by construction of the launch
+        const int n = C * cstride;
+        for (int i = threadIdx.x; i < n; i += K2_TH * K2_TW) {
+            const int c = i / cstride, r = i - c * cstride;
+            const int yy = r / in_tw, xx = r - yy * in_tw;
+            const size_t g = ((size_t)b * C + c) * hw + (size_t)(ys0 + yy) * w + xs0 + xx;
+            if (sim) tile[c * cstride + r] = __ldg(sim + g);
+            if (logits) tile[C * tile_cap + c * cstride + r] = __ldg(logits + g);
+        }
+        __syncthreads();
+    }
+    if (Y >= H || X >= W) return;
     Taps t;
     {
         const float ys = __fmul_rn(ry, (float)Y), xs = __fmul_rn(rx, (float)X);
@@ -193,24 +249,25 @@ __global__ void __launch_bounds__(128) upsample_label_fuse_kernel(const float* _
         t.hy = __fsub_rn(1.f, t.ly);
         t.lx = __fsub_rn(xs, (float)x0);
         t.hx = __fsub_rn(1.f, t.lx);
-        t.o00 = y0 * w + x0;
-        t.o01 = y0 * w + x1;
-        t.o10 = y1 * w + x0;
-        t.o11 = y1 * w + x1;
+        t.o00 = (y0 - ys0) * in_tw + (x0 - xs0);
+        t.o01 = (y0 - ys0) * in_tw + (x1 - xs0);
+        t.o10 = (y1 - ys0) * in_tw + (x0 - xs0);
+        t.o11 = (y1 - ys0) * in_tw + (x1 - xs0);
     }
-    const int hw = h * w;
     const size_t o = ((size_t)b * H + Y) * W + X;
     int lr = -1, lc = -2;
     if (sim) {
-        float c;
-        upsample_softmax_max<true>(sim + (size_t)b * C * hw, C, hw, t, temp, c, lr);
-        if (conf_rep) conf_rep[o] = c;
+        float cf;
+        if (STAGED) upsample_softmax_max<true>(tile, C, cstride, t, temp, cf, lr);
+        else upsample_softmax_max<true>(sim + (size_t)b * C * hw, C, hw, t, temp, cf, lr);
+        if (conf_rep) conf_rep[o] = cf;
         if (label_rep) label_rep[o] = lr;
     }
     if (logits) {
-        float c;
-        upsample_softmax_max<false>(logits + (size_t)b * C * hw, C, hw, t, 1.f, c, lc);
-        if (conf_cls) conf_cls[o] = c;
+        float cf;
+        if (STAGED) upsample_softmax_max<false>(tile + C * tile_cap, C, cstride, t, 1.f, cf, lc);
+        else upsample_softmax_max<false>(logits + (size_t)b * C * hw, C, hw, t, 1.f, cf, lc);
+        if (conf_cls) conf_cls[o] = cf;
         if (label_cls) label_cls[o] = lc;
     }
     if (fused && fuse_mode == CSS_FUSE_MIX) fused[o] = (lr == lc) ? (float)lc : 255.f;   // ddp_model.py:115-118
@@ -226,13 +283,29 @@ extern "C" int css_upsample_label_fuse(const float* sim, const float* logits, fl
     CSS_CHECK_ARG(logits || (!conf_cls && !label_cls), CSS_E_ARG, "css_upsample_label_fuse: cls outputs without logits");
     CSS_CHECK_ARG(fuse_mode == CSS_FUSE_NONE || (fuse_mode == CSS_FUSE_MIX && sim && logits && fused), CSS_E_ARG,
                   "css_upsample_label_fuse: mix fusion needs sim, logits and fused");
-    CSS_CHECK_ARG(B <= 65535 && (long long)H * W < (1ll << 31), CSS_E_SIZE, "css_upsample_label_fuse: B or H*W too large");
+    CSS_CHECK_ARG(B <= 65535 && (H + K2_TH - 1) / K2_TH <= 65535 && (long long)B * C * h * w < (1ll << 31), CSS_E_SIZE,
+                  "css_upsample_label_fuse: B, H or the map too large");
     // area_pixel_compute_scale(align_corners=True): (in-1)/(out-1) in fp32, 0 when out == 1
     const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    dim3 grid((H * W + 127) / 128, B);
-    upsample_label_fuse_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(sim, logits, temp, fuse_mode, C, h, w, H, W, ry, rx,
-                                                                       conf_rep, label_rep, conf_cls, label_cls, fused);
+    // upper bound of the low-res footprint of one 8 x 32 output tile (+1 of slack for fp32 rounding of src indices)
+    const int in_th = (int)fminf((float)h, ceilf(ry * (K2_TH - 1)) + 3.f);
+    const int in_tw = (int)fminf((float)w, ceilf(rx * (K2_TW - 1)) + 3.f);
+    const int tile_cap = in_th * in_tw;
+    const size_t smem = (size_t)2 * C * tile_cap * sizeof(float);
+    dim3 grid((W + K2_TW - 1) / K2_TW, (H + K2_TH - 1) / K2_TH, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem <= 96 * 1024) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) { css_set_error("css_upsample_label_fuse: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        upsample_label_fuse_kernel<true><<<grid, K2_TH * K2_TW, smem, st>>>(sim, logits, temp, fuse_mode, C, h, w, H, W, ry, rx, tile_cap,
+                                                                            conf_rep, label_rep, conf_cls, label_cls, fused);
+    } else {   // strong down-sampling: the footprint does not fit, read the taps from global memory
+        upsample_label_fuse_kernel<false><<<grid, K2_TH * K2_TW, 0, st>>>(sim, logits, temp, fuse_mode, C, h, w, H, W, ry, rx, 0,
+                                                                          conf_rep, label_rep, conf_cls, label_cls, fused);
+    }
     CSS_CHECK_LAUNCH("css_upsample_label_fuse", 1);
     return 0;
 }

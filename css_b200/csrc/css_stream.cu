@@ -107,14 +107,45 @@ __global__ void __launch_bounds__(ST_THREADS) stream_rep_kernel(const float* __r
     if (tid == 0) touched[blockIdx.x] = seen;
 }
 
-// deterministic second stage: thread (c, d) adds the partials of the CTAs that touched class c, in CTA order
+// deterministic second stage: block c first compacts the ids of the CTAs that touched class c (ballot order = CTA order),
+// then thread d adds their partials 8 loads at a time, always in the same order.
 __global__ void __launch_bounds__(CSS_D) stream_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
                                                               const int32_t* __restrict__ meta, int G, int C,
                                                               float* __restrict__ class_stats) {
-    const int c = blockIdx.x, d = threadIdx.x;
+    extern __shared__ int glist[];                 // [G]
+    __shared__ int wtot[CSS_D / 32];
+    __shared__ int n_list;
+    const int c = blockIdx.x, d = threadIdx.x, warp = d >> 5, lane = d & 31;
+    if (d == 0) n_list = 0;
+    __syncthreads();
+    for (int base = 0; base < G; base += CSS_D) {
+        const int g = base + d;
+        const bool on = g < G && ((touched[g] >> c) & 1u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();
+        int off = n_list;
+        for (int w2 = 0; w2 < warp; ++w2) off += wtot[w2];
+        if (on) glist[off + __popc(bal & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        if (d == 0) {
+            int t = 0;
+            for (int w2 = 0; w2 < CSS_D / 32; ++w2) t += wtot[w2];
+            n_list += t;
+        }
+        __syncthreads();
+    }
+    const int n = n_list;
     float acc = 0.f;
-    for (int g = 0; g < G; ++g)
-        if ((touched[g] >> c) & 1u) acc += partials[((size_t)g * C + c) * CSS_D + d];
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partials[((size_t)glist[i + u] * C + c) * CSS_D + d];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; i < n; ++i) acc += partials[((size_t)glist[i] * C + c) * CSS_D + d];
     class_stats[c * (CSS_D + 1) + d] = acc;
     if (d == 0) class_stats[c * (CSS_D + 1) + CSS_D] = (float)meta[CSS_META_N_VALID + c];
 }
@@ -137,7 +168,7 @@ extern "C" int css_stream_rep(const void* rep, int rep_dtype, const uint32_t* va
         if (e != cudaSuccess) { css_set_error("css_stream_rep: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     stream_rep_kernel<<<G, ST_THREADS, smem, st>>>((const float*)rep, valid_bits, C, hw, N, rows_hat, norms, partials, touched);
-    stream_reduce_kernel<<<C, CSS_D, 0, st>>>(partials, touched, meta, G, C, class_stats);
+    stream_reduce_kernel<<<C, CSS_D, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
     CSS_CHECK_LAUNCH("css_stream_rep", 2);
     return 0;
 }

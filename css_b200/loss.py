@@ -82,9 +82,16 @@ class _ContrastFn(torch.autograd.Function):
         loss = torch.empty((), device=dev, dtype=torch.float32)
         a_idx, n_idx = (None, None) if indices is None else indices
         seed, offset = mod._next_draw_key()
+        ev = mod.score_events
+        if ev is not None:                       # bench.py times the dominant kernel live, on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib.css_score_ce(ptr(ws.rows_hat), ptr(ws.norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
                                ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, N, C, D, Q, Nn,
                                float(mod.temp), ptr(ws.loss_kq), ptr(anchor_px), ptr(grad_anchor), ptr(loss), st), "css_score_ce")
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         ctx.shape = (B2, D, h, w)
         ctx.n_anchor = C * Q
         ctx.save_for_backward(anchor_px, grad_anchor)
@@ -124,6 +131,7 @@ class Contrast_Loss(nn.Module):
         self._step = 0
         self._ws = None
         self.last = None
+        self.score_events = None              # set to a list to collect (start, end) CUDA events around css_score_ce
 
     # ---- sampler state: (seed, offset) of the device Philox stream; one offset per forward call -------------------
     def set_sampler(self, seed, step=0):

@@ -155,6 +155,16 @@ def test_multi_hot_labels_and_empty_batch():
     assert crit.selection()["V"] == 0 and torch.equal(protos, torch.ones(C, 256).cuda())
 
 
+def uniform_pvalue(idx, n, max_bins=8):
+    """chi-square p-value of `idx` being uniform on [0, n), with coarse bins whose expected mass follows their width."""
+    from scipy import stats
+    bins = min(max_bins, n)
+    which = (np.arange(n, dtype=np.int64) * bins) // n
+    width = np.bincount(which, minlength=bins).astype(np.float64)
+    cnt = np.bincount(which[np.asarray(idx, dtype=np.int64)], minlength=bins)
+    return stats.chisquare(cnt, width / width.sum() * cnt.sum()).pvalue
+
+
 def test_sampler_distributions():
     """chi-square tests of the device Philox sampler: anchor uniformity, class histogram vs
     softmax(cos(P_k,P_j)/temp), uniformity inside a class."""
@@ -176,9 +186,7 @@ def test_sampler_distributions():
         if sel["n_hard"][k] == 0:
             continue
         # (a) anchors uniform over the hard list (coarse bins so that expected counts are large)
-        bins = min(8, sel["n_hard"][k])
-        cnt = np.bincount((a[k].astype(np.int64) * bins) // sel["n_hard"][k], minlength=bins)
-        assert stats.chisquare(cnt).pvalue > 1e-4
+        assert uniform_pvalue(a[k], sel["n_hard"][k]) > 1e-4
         # (b) class histogram of the negatives vs proto_prob
         others = sel["num_list"][k + 1:] + sel["num_list"][:k]
         edges = np.concatenate([[0], np.cumsum(others)])
@@ -189,9 +197,7 @@ def test_sampler_distributions():
         # (c) uniform inside the largest segment
         j = int(np.argmax(others))
         inside = n[k].reshape(-1)[seg == j] - edges[j]
-        bins = min(8, others[j])
-        cnt = np.bincount((inside.astype(np.int64) * bins) // others[j], minlength=bins)
-        assert stats.chisquare(cnt).pvalue > 1e-4
+        assert uniform_pvalue(inside, others[j]) > 1e-4
 
 
 def test_full_size_properties_voc_batch():
