@@ -4,13 +4,15 @@
 //
 // Every query draws its own Nn negatives (loss.py:137-142), so this is a per-query row gather (1 KB fp32 rows of the
 // pixel-major normalised copy written by css_stream_rep), not a shared-operand GEMM: 2*D flops per 4*D gathered bytes.
-// It is bound by L2/HBM gather bandwidth, not by the FMA or tensor pipes.
+// It is bound by the L2 -> SM gather path (the 107 MB copy is mostly L2 resident at VOC size), not by the tensor pipe.
 //
-// Work split: one warp per (present-class slot k, query q).  The warp is four 8-lane groups; a group owns one candidate
-// row at a time (8 lanes x 8 x 128-bit loads = the 1 KB row, each 128 B line read by one 8-lane group), reduces the dot
-// with 3 shuffles, and keeps an online-softmax state (m, l, sum_j e^{z_j-m} r_hat_j) in registers, so the backward never
-// re-gathers.  Candidate row ids for the next 32 candidates are produced one per lane (Philox draw or fed index ->
-// rotated segment -> class list lookup) and handed to the groups by shuffle.
+// Work split: one CTA (4 warps) per (present-class slot k, query q); warp w owns candidates j = w, w+4, ...  A warp is
+// four 8-lane groups; a group owns one candidate row at a time (8 lanes x 8 x 128-bit loads = the 1 KB row, every 128 B
+// line read by exactly one group), reduces the dot with 3 shuffles and keeps an online-softmax state
+// (m, l, sum_j 2^{z_j-m} r_hat_j) in registers, so the backward never re-gathers.  Packed fp32x2 FMAs (FFMA2, sm_100)
+// halve the FMA issue slots of the dot and of the weighted row accumulation.  Candidate row ids for the next 32
+// candidates are produced one per lane (Philox draw or fed index -> rotated segment -> class list lookup) and handed to
+// the groups by shuffle.  The four warp states are merged through shared memory in a fixed order (deterministic).
 #include "css_common.cuh"
 
 #define SC_WARPS 4
@@ -35,16 +37,26 @@ __device__ __forceinline__ int draw_anchor(const DrawKey& dk, int k, int q, int 
     return (int)__umulhi(r.x, (uint32_t)n_hard);
 }
 
-// negative draw j in [0, Nn): class ~ Categorical(cdf row), index ~ Uniform inside that class's valid list; returned as
-// an index into the rotated concatenation of the valid lists (loss.py:136-142)
-__device__ __forceinline__ int draw_negative(const DrawKey& dk, int k, int q, int j, int V, const float* cdf_row,
-                                             const int* rot_off) {
+// first i in [0, 31] with tab[i] > u  (tab is non-decreasing and tab[31] > u): 5-step binary search
+template <typename T>
+__device__ __forceinline__ int upper_bound32(const T* tab, T u) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (tab[lo + step - 1] <= u) lo += step;
+    return lo;
+}
+
+// negative draw j in [0, Nn): class ~ Categorical(cdf row), index ~ Uniform inside that class's valid list (loss.py:136-142).
+// Returns the index inside the class list and the rotated segment `seg`; rot_off[seg] + index is the reference's index
+// into the rotated concatenation of the valid lists.
+__device__ __forceinline__ int draw_negative(const DrawKey& dk, int k, int q, int j, const float* cdf_row, const int* rot_off,
+                                             int& seg) {
     const uint4 r = Philox::run(make_uint4((uint32_t)j, ((uint32_t)k << 24) | (uint32_t)q, dk.off_lo, dk.off_hi), dk.key);
     const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-    int i = 0;
-    while (i < V - 2 && u >= cdf_row[i]) ++i;
-    const int n = rot_off[i + 1] - rot_off[i];
-    return rot_off[i] + (int)__umulhi(r.y, (uint32_t)n);
+    seg = upper_bound32(cdf_row, u);                       // cdf_row[i] == 1 for i >= V-2, u < 1
+    const int n = rot_off[seg + 1] - rot_off[seg];
+    return (int)__umulhi(r.y, (uint32_t)n);
 }
 
 // per-slot tables shared by the sampler and the scorer: rotated class order k+1..V-1,0..k-1, prefix offsets, CDF row
@@ -91,10 +103,13 @@ __global__ void __launch_bounds__(256) sample_kernel(const int32_t* __restrict__
     const long long total = (long long)Q * (Nn + 1);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int q = (int)(i / (Nn + 1)), j = (int)(i - (long long)q * (Nn + 1));
-        if (j == 0)
+        if (j == 0) {
             anchor_idx[k * Q + q] = draw_anchor(dk, k, q, n_hard);
-        else
-            neg_idx[((size_t)k * Q + q) * Nn + (j - 1)] = draw_negative(dk, k, q, j - 1, V, tb.cdf, tb.rot_off);
+        } else {
+            int seg;
+            const int within = draw_negative(dk, k, q, j - 1, tb.cdf, tb.rot_off, seg);
+            neg_idx[((size_t)k * Q + q) * Nn + (j - 1)] = tb.rot_off[seg] + within;
+        }
     }
 }
 
@@ -123,23 +138,23 @@ __device__ __forceinline__ float group_sum8(float v) {     // reduce over the 8 
     return v;
 }
 
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// 32-element slice dot with packed fp32x2 FMAs, 4 independent chains
 __device__ __forceinline__ float dot8(const float4 (&a)[8], const float4 (&r)[8]) {
-    float s0 = 0.f, s1 = 0.f;
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-        s0 = fmaf(a[i].x, r[i].x, s0);
-        s0 = fmaf(a[i].y, r[i].y, s0);
-        s0 = fmaf(a[i].z, r[i].z, s0);
-        s0 = fmaf(a[i].w, r[i].w, s0);
-        s1 = fmaf(a[i + 1].x, r[i + 1].x, s1);
-        s1 = fmaf(a[i + 1].y, r[i + 1].y, s1);
-        s1 = fmaf(a[i + 1].z, r[i + 1].z, s1);
-        s1 = fmaf(a[i + 1].w, r[i + 1].w, s1);
+        s0 = __ffma2_rn(lo2(a[i]), lo2(r[i]), s0);
+        s1 = __ffma2_rn(hi2(a[i]), hi2(r[i]), s1);
+        s2 = __ffma2_rn(lo2(a[i + 1]), lo2(r[i + 1]), s2);
+        s3 = __ffma2_rn(hi2(a[i + 1]), hi2(r[i + 1]), s3);
     }
-    return s0 + s1;
+    return ((s0.x + s0.y) + (s1.x + s1.y)) + ((s2.x + s2.y) + (s3.x + s3.y));
 }
 
-struct Online {            // online softmax state of one 8-lane group
+struct Online {            // online softmax state (base 2) of one 8-lane group
     float m, l;
     float4 acc[8];
 };
@@ -147,7 +162,7 @@ struct Online {            // online softmax state of one 8-lane group
 template <bool WANT_GRAD>
 __device__ __forceinline__ void online_update(Online& st, float z, bool valid, const float4 (&r)[8]) {
     if (valid && z > st.m) {                       // group-uniform; rare after the first few rows
-        const float sc = expf(st.m - z);         // m = -inf -> 0
+        const float sc = exp2f(st.m - z);          // m = -inf -> 0
         st.l *= sc;
         if (WANT_GRAD) {
 #pragma unroll
@@ -160,42 +175,42 @@ __device__ __forceinline__ void online_update(Online& st, float z, bool valid, c
         }
         st.m = z;
     }
-    const float wgt = valid ? expf(z - st.m) : 0.f;
+    const float wgt = valid ? exp2f(z - st.m) : 0.f;
     st.l += wgt;
     if (WANT_GRAD) {
+        const float2 ww = make_float2(wgt, wgt);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            st.acc[i].x = fmaf(wgt, r[i].x, st.acc[i].x);
-            st.acc[i].y = fmaf(wgt, r[i].y, st.acc[i].y);
-            st.acc[i].z = fmaf(wgt, r[i].z, st.acc[i].z);
-            st.acc[i].w = fmaf(wgt, r[i].w, st.acc[i].w);
+            const float2 lo = __ffma2_rn(ww, lo2(r[i]), lo2(st.acc[i]));
+            const float2 hi = __ffma2_rn(ww, hi2(r[i]), hi2(st.acc[i]));
+            st.acc[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
     }
 }
 
 template <bool WANT_GRAD>
-__global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(
+__global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel(
     const float4* __restrict__ rows_hat, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
     uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
     float4* __restrict__ grad_anchor) {
     __shared__ SlotTables tb;
-    const int k = blockIdx.y;
+    __shared__ float4 s_acc[SC_WARPS][CSS_D / 4];
+    __shared__ float s_m[SC_WARPS], s_l[SC_WARPS], s_pos[2];
+    const int k = blockIdx.y, q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * SC_WARPS + warp;
     const int V = meta[CSS_META_V];
     const int c = (k < V) ? meta[CSS_META_CLS_OF_SLOT + k] : 0;
     const int n_hard = (k < V) ? meta[CSS_META_N_HARD + c] : 0;
     if (k >= V || V <= 1 || n_hard == 0) {         // absent slot / degenerate batch / no hard pixel (loss.py:116,125-130)
-        if (q < Q && lane == 0) {
+        if (threadIdx.x == 0) {
             loss_kq[k * Q + q] = 0.f;
             anchor_px[k * Q + q] = -1;
         }
         return;
     }
     build_slot_tables(tb, meta, class_cdf, k, V);
-    if (q >= Q) return;
 
     const int grp = lane >> 3, l8 = lane & 7;
     const DrawKey dk = make_key(seed, offset);
@@ -208,6 +223,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(
         for (int i = 0; i < 8; ++i) a[i] = __ldg(ap + i * 8);
     }
     const float4* pp = proto_hat + (size_t)c * (CSS_D / 4) + l8;
+    const float scale2 = 1.4426950408889634f / temp;          // logits in base 2: z2 = cos * log2(e) / temp
 
     Online st;
     st.m = -INFINITY;
@@ -216,55 +232,55 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(
     for (int i = 0; i < 8; ++i) st.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float z0 = 0.f, cos_pos = 0.f;
 
-    const int n_cand = Nn + 1;                     // candidate 0 = the (updated) prototype of class c (loss.py:143-144)
-    for (int base = 0; base < n_cand; base += 32) {
+    // warp w owns candidates j = w + 4 n; candidate 0 = the (updated) prototype of class c (loss.py:143-144)
+    const int n_cand = Nn + 1;
+    const int cnt = (n_cand - warp + SC_WARPS - 1) / SC_WARPS;
+    for (int base = 0; base < cnt; base += 32) {
         // one candidate row id per lane: -1 = prototype, -2 = past the end
         int my_row = -2;
         {
-            const int j = base + lane;
+            const int n = base + lane;
+            const int j = warp + SC_WARPS * n;
             if (j == 0) {
                 my_row = -1;
-            } else if (j < n_cand) {
-                const int idx = neg_idx ? neg_idx[((size_t)k * Q + q) * Nn + (j - 1)]
-                                        : draw_negative(dk, k, q, j - 1, V, tb.cdf, tb.rot_off);
-                int i = 0;
-                while (i < V - 2 && idx >= tb.rot_off[i + 1]) ++i;
-                my_row = valid_list[(size_t)tb.rot_cls[i] * N + (idx - tb.rot_off[i])];
+            } else if (n < cnt) {
+                int seg, within;
+                if (neg_idx) {
+                    const int idx = neg_idx[((size_t)k * Q + q) * Nn + (j - 1)];
+                    seg = upper_bound32(tb.rot_off + 1, idx);          // largest seg with rot_off[seg] <= idx
+                    within = idx - tb.rot_off[seg];
+                } else {
+                    within = draw_negative(dk, k, q, j - 1, tb.cdf, tb.rot_off, seg);
+                }
+                my_row = valid_list[(size_t)tb.rot_cls[seg] * N + within];
             }
         }
+        const int steps = min(8, (cnt - base + 3) >> 2);
 #pragma unroll 1
-        for (int t = 0; t < 8; t += 2) {
-            const int row0 = __shfl_sync(0xffffffffu, my_row, t * 4 + grp);
-            const int row1 = __shfl_sync(0xffffffffu, my_row, (t + 1) * 4 + grp);
-            const float4* p0 = (row0 >= 0) ? rows_hat + (size_t)row0 * (CSS_D / 4) + l8 : pp;
-            const float4* p1 = (row1 >= 0) ? rows_hat + (size_t)row1 * (CSS_D / 4) + l8 : pp;
-            float4 r0[8], r1[8];
+        for (int t = 0; t < steps; ++t) {
+            const int row = __shfl_sync(0xffffffffu, my_row, t * 4 + grp);
+            const float4* p = (row >= 0) ? rows_hat + (size_t)row * (CSS_D / 4) + l8 : pp;
+            float4 r[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r0[i] = __ldg(p0 + i * 8);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r1[i] = __ldg(p1 + i * 8);
-            const float cos0 = group_sum8(dot8(a, r0));
-            const float cos1 = group_sum8(dot8(a, r1));
-            const float zz0 = __fdiv_rn(cos0, temp), zz1 = __fdiv_rn(cos1, temp);
-            if (row0 == -1) {
-                z0 = zz0;
-                cos_pos = cos0;
+            for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
+            const float cosv = group_sum8(dot8(a, r));
+            const float z = cosv * scale2;
+            if (row == -1) {
+                z0 = z;
+                cos_pos = cosv;
             }
-            online_update<WANT_GRAD>(st, zz0, row0 != -2, r0);
-            online_update<WANT_GRAD>(st, zz1, row1 != -2, r1);
+            online_update<WANT_GRAD>(st, z, row != -2, r);
         }
     }
 
-    // merge the four groups (xor 8, xor 16); afterwards every lane holds the full state for its column slice
-    z0 = __shfl_sync(0xffffffffu, z0, 0);
-    cos_pos = __shfl_sync(0xffffffffu, cos_pos, 0);
+    // merge the four groups (xor 8, xor 16); afterwards every lane holds the warp's state for its column slice
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
         const float m_o = __shfl_xor_sync(0xffffffffu, st.m, o);
         const float l_o = __shfl_xor_sync(0xffffffffu, st.l, o);
         const float M = fmaxf(st.m, m_o);
-        const float s_a = (st.m == -INFINITY) ? 0.f : expf(st.m - M);
-        const float s_b = (m_o == -INFINITY) ? 0.f : expf(m_o - M);
+        const float s_a = (st.m == -INFINITY) ? 0.f : exp2f(st.m - M);
+        const float s_b = (m_o == -INFINITY) ? 0.f : exp2f(m_o - M);
         st.l = st.l * s_a + l_o * s_b;
         if (WANT_GRAD) {
 #pragma unroll
@@ -277,41 +293,74 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(
         }
         st.m = M;
     }
-    // CE with target 0: logsumexp(z) - z_0 (loss.py:147)
     if (lane == 0) {
-        loss_kq[k * Q + q] = (st.m + logf(st.l)) - z0;
+        s_m[warp] = st.m;
+        s_l[warp] = st.l;
+        if (warp == 0) {
+            s_pos[0] = z0;
+            s_pos[1] = cos_pos;
+        }
+    }
+    if (WANT_GRAD && grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_acc[warp][i * 8 + l8] = st.acc[i];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+
+    // warp 0 merges the SC_WARPS warp states in warp order
+    float M = s_m[0];
+#pragma unroll
+    for (int w2 = 1; w2 < SC_WARPS; ++w2) M = fmaxf(M, s_m[w2]);
+    float sc[SC_WARPS], l = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < SC_WARPS; ++w2) {
+        sc[w2] = (s_m[w2] == -INFINITY) ? 0.f : exp2f(s_m[w2] - M);
+        l += s_l[w2] * sc[w2];
+    }
+    // CE with target 0: logsumexp(z) - z_0 (loss.py:147), evaluated in base 2
+    if (lane == 0) {
+        loss_kq[k * Q + q] = 0.6931471805599453f * ((M + log2f(l)) - s_pos[0]);
         anchor_px[k * Q + q] = pa;
     }
     if (WANT_GRAD) {
         // dL/da = (sum_j g_j r_hat_j - (sum_j g_j cos_j) a_hat) / max(||a||, eps),  g_j = (pi_j - [j==0]) / (Q V temp)
         // with sum_j pi_j r_hat_j = acc / l and sum_j pi_j cos_j = a_hat . (acc / l)        
-        const float inv_l = 1.f / st.l;
-        float4 ph[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ph[i] = __ldg(pp + i * 8);
+        const float inv_l = 1.f / l;
+        const float4* ap = rows_hat + (size_t)pa * (CSS_D / 4);
+        const float4* php = proto_hat + (size_t)c * (CSS_D / 4);
+        float4 S[2], av[2], ph[2];
         float sdot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            st.acc[i].x *= inv_l;
-            st.acc[i].y *= inv_l;
-            st.acc[i].z *= inv_l;
-            st.acc[i].w *= inv_l;
-        }
-        sdot = group_sum8(dot8(a, st.acc));
-        const float scale = 1.f / ((float)Q * (float)V * temp);
-        const float tt = (sdot - cos_pos) * scale;
-        const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);
-        if (grp == 0) {
-            float4* g = grad_anchor + ((size_t)k * Q + q) * (CSS_D / 4) + l8;
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int col = lane + 32 * h2;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 o;
-                o.x = ((st.acc[i].x - ph[i].x) * scale - tt * a[i].x) * inv_na;
-                o.y = ((st.acc[i].y - ph[i].y) * scale - tt * a[i].y) * inv_na;
-                o.z = ((st.acc[i].z - ph[i].z) * scale - tt * a[i].z) * inv_na;
-                o.w = ((st.acc[i].w - ph[i].w) * scale - tt * a[i].w) * inv_na;
-                g[i * 8] = o;
+            for (int w2 = 0; w2 < SC_WARPS; ++w2) {
+                const float4 v = s_acc[w2][col];
+                t.x = fmaf(v.x, sc[w2], t.x);
+                t.y = fmaf(v.y, sc[w2], t.y);
+                t.z = fmaf(v.z, sc[w2], t.z);
+                t.w = fmaf(v.w, sc[w2], t.w);
             }
+            S[h2] = make_float4(t.x * inv_l, t.y * inv_l, t.z * inv_l, t.w * inv_l);
+            av[h2] = __ldg(ap + col);
+            ph[h2] = __ldg(php + col);
+            sdot += S[h2].x * av[h2].x + S[h2].y * av[h2].y + S[h2].z * av[h2].z + S[h2].w * av[h2].w;
+        }
+        sdot = warp_sum(sdot);
+        const float scale = 1.f / ((float)Q * (float)V * temp);
+        const float tt = (sdot - s_pos[1]) * scale;
+        const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);
+        float4* g = grad_anchor + ((size_t)k * Q + q) * (CSS_D / 4);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            float4 o;
+            o.x = ((S[h2].x - ph[h2].x) * scale - tt * av[h2].x) * inv_na;
+            o.y = ((S[h2].y - ph[h2].y) * scale - tt * av[h2].y) * inv_na;
+            o.z = ((S[h2].z - ph[h2].z) * scale - tt * av[h2].z) * inv_na;
+            o.w = ((S[h2].w - ph[h2].w) * scale - tt * av[h2].w) * inv_na;
+            g[lane + 32 * h2] = o;
         }
     }
 }
@@ -343,9 +392,10 @@ extern "C" int css_score_ce(const float* rows_hat, const float* norms, const flo
     CSS_CHECK_ARG((anchor_idx == nullptr) == (neg_idx == nullptr), CSS_E_ARG,
                   "css_score_ce: anchor_idx and neg_idx must be fed together");
     CSS_CHECK_ARG(N > 0 && Q > 0 && Nn > 0 && Q < (1 << 24), CSS_E_ARG, "css_score_ce: bad N/Q/Nn");
+    CSS_CHECK_ARG(Q <= 65535 * 32768, CSS_E_SIZE, "css_score_ce: Q too large");
     if (int e = css_check_dims(C, D)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((Q + SC_WARPS - 1) / SC_WARPS, C);
+    dim3 grid(Q, C);
     if (grad_anchor)
         score_ce_kernel<true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows_hat, norms, (const float4*)proto_hat, class_cdf,
                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,

@@ -1,0 +1,112 @@
+"""Per-op device timings (CUDA events, inputs rotated through > L2-sized pools so every launch reads cold HBM).
+Development aid for kernel tuning:  python tools/kbench.py [--workload voc321_mix] [--iters 50]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import css_b200  # noqa: E402
+from css_b200 import _lib  # noqa: E402
+from bench import WORKLOADS, make_inputs  # noqa: E402
+
+
+def timeit(fn, iters, warm=3):
+    """Device time per call: `iters` calls are captured into ONE CUDA graph (no host launch overhead in the number)."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3     # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="voc321_mix")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--pool", type=int, default=4)
+    a = ap.parse_args()
+    cfg = WORKLOADS[a.workload]
+    B, C, h, w, H, W, Q, Nn, temp = (cfg[k] for k in ("B", "C", "h", "w", "H", "W", "Q", "Nn", "temp"))
+    host = make_inputs(cfg, 0)
+    dev = torch.device("cuda")
+    P = a.pool
+    rep_u = [host["rep_u"].to(dev) + 0 for _ in range(P)]
+    rep_all = [host["rep_all"].to(dev) + 0 for _ in range(P)]
+    pred_u = host["pred_u"].to(dev)
+    label, mask = host["label"].to(dev), host["mask"].to(dev)
+    protos = host["prototypes"].to(dev)
+    res = {}
+    res["sim_map teacher (cos)"] = timeit(lambda i: css_b200.ops.cos_sim_map(rep_u[i % P], protos), a.iters)
+    res["sim_map student (softmax)"] = timeit(lambda i: css_b200.ops.proto_softmax_sim(rep_all[i % P], protos, temp), a.iters)
+    sim = css_b200.ops.cos_sim_map(rep_u[0], protos)
+    res["upsample_label_fuse (mix)"] = timeit(lambda i: css_b200.ops.upsample_label_fuse(sim, pred_u, temp, (H, W), "mix"), a.iters)
+    prob = css_b200.ops.proto_softmax_sim(rep_all[0], protos, temp)
+    crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=cfg["strong"], seed=1).cuda()
+    with torch.no_grad():
+        crit(rep_all[0], label, mask, prob, protos.clone())
+    ws = crit.last["ws"]
+    lib = _lib.load()
+    from css_b200._lib import ptr, stream_ptr, check
+    N = ws.N
+    D = 256
+    B2 = 2 * B
+
+    def select(i):
+        check(lib.css_select(ptr(label), ptr(mask), ptr(prob), float(cfg["strong"]), B2, C, h, w, ptr(ws.valid_bits), ptr(ws.hard_bits),
+                             ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), stream_ptr()), "select")
+
+    def stream(i):
+        check(lib.css_stream_rep(ptr(rep_all[i % P]), 0, ptr(ws.valid_bits), ptr(ws.meta), B2, C, D, h, w, ptr(ws.rows_hat),
+                                 ptr(ws.norms), ptr(ws.partials), ptr(ws.touched), ptr(ws.class_stats), stream_ptr()), "stream")
+
+    p2 = protos.clone()
+
+    def ema(i):
+        check(lib.css_proto_ema(ptr(p2), ptr(ws.class_stats), ptr(ws.meta), 0.99, 0.01, temp, C, D, ptr(ws.proto_hat),
+                                ptr(ws.class_cdf), stream_ptr()), "ema")
+
+    anchor_px = torch.empty(C * Q, device=dev, dtype=torch.int32)
+    grad_anchor = torch.empty(C * Q * D, device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev)
+
+    def score(i, grad=True):
+        check(lib.css_score_ce(ptr(ws.rows_hat), ptr(ws.norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+                               ptr(ws.hard_list), ptr(ws.meta), None, None, 7, i, N, C, D, Q, Nn, temp, ptr(ws.loss_kq),
+                               ptr(anchor_px), ptr(grad_anchor) if grad else None, ptr(loss), stream_ptr()), "score")
+
+    grads = [torch.empty(B2, D, h, w, device=dev) for _ in range(P)]
+    one = torch.ones((), device=dev)
+
+    def scatter(i):
+        check(lib.css_grad_scatter(ptr(one), ptr(anchor_px), ptr(grad_anchor), C * Q, B2, D, h, w, ptr(grads[i % P]), stream_ptr()), "scatter")
+
+    res["select (3 kernels)"] = timeit(select, a.iters)
+    res["stream_rep (+reduce)"] = timeit(stream, a.iters)
+    res["proto_ema (+cdf)"] = timeit(ema, a.iters)
+    res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
+    res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
+    res["grad_scatter (+memset)"] = timeit(scatter, a.iters)
+    tot = sum(v for k, v in res.items() if k != "score_ce fwd only")
+    for k, v in res.items():
+        print(f"{k:34s} {v:9.1f} us")
+    print(f"{'sum (path)':34s} {tot:9.1f} us")
+    print(json.dumps({"workload": a.workload, "us": res}))
+
+
+if __name__ == "__main__":
+    main()
