@@ -29,8 +29,9 @@ SIGNATURES = {
     "css_upsample_label_fuse": (c_int, [P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "css_select_tiles": (c_int, [c_int]),
     "css_select": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
-    "css_stream_blocks": (c_int, []),
-    "css_stream_rep": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "css_rep_pass": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P]),
+    "css_class_blocks": (c_int, [c_int]),
+    "css_class_stats": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, P, P, P]),
     "css_sample": (c_int, [P, P, c_uint64, c_uint64, c_int, c_int, c_int, P, P, P]),
     "css_score_ce": (c_int, [P, P, P, P, P, P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_int, c_int, c_int, c_float,

@@ -3,7 +3,7 @@
 // Reference: generalframeworks/loss/loss.py:124-149 (+ negative_index_sampler :410-418) and its autograd backward.
 //
 // Every query draws its own Nn negatives (loss.py:137-142), so this is a per-query row gather (1 KB fp32 rows of the
-// pixel-major normalised copy written by css_stream_rep), not a shared-operand GEMM: 2*D flops per 4*D gathered bytes.
+// pixel-major copy written by css_rep_pass, scaled by 1/max(||r||,1e-8) on the fly), not a shared-operand GEMM: 2*D flops per 4*D gathered bytes.
 // It is bound by the L2 -> SM gather path (the 107 MB copy is mostly L2 resident at VOC size), not by the tensor pipe.
 //
 // Work split: one CTA (4 warps) per (present-class slot k, query q); warp w owns candidates j = w, w+4, ...  A warp is
@@ -159,8 +159,9 @@ struct Online {            // online softmax state (base 2) of one 8-lane group
     float4 acc[8];
 };
 
+// `inv_nr` = 1 / max(||r||, 1e-8): the rows are stored raw, the state accumulates sum_j 2^{z_j-m} r_j / ||r_j||
 template <bool WANT_GRAD>
-__device__ __forceinline__ void online_update(Online& st, float z, bool valid, const float4 (&r)[8]) {
+__device__ __forceinline__ void online_update(Online& st, float z, bool valid, float inv_nr, const float4 (&r)[8]) {
     if (valid && z > st.m) {                       // group-uniform; rare after the first few rows
         const float sc = exp2f(st.m - z);          // m = -inf -> 0
         st.l *= sc;
@@ -178,7 +179,8 @@ __device__ __forceinline__ void online_update(Online& st, float z, bool valid, c
     const float wgt = valid ? exp2f(z - st.m) : 0.f;
     st.l += wgt;
     if (WANT_GRAD) {
-        const float2 ww = make_float2(wgt, wgt);
+        const float wr = wgt * inv_nr;
+        const float2 ww = make_float2(wr, wr);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 lo = __ffma2_rn(ww, lo2(r[i]), lo2(st.acc[i]));
@@ -188,9 +190,9 @@ __device__ __forceinline__ void online_update(Online& st, float z, bool valid, c
     }
 }
 
-template <bool WANT_GRAD>
-__global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel(
-    const float4* __restrict__ rows_hat, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
+template <bool WANT_GRAD, bool PREFETCH>
+__global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel(
+    const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
     uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
@@ -218,10 +220,11 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel
     const int pa = hard_list[(size_t)c * N + ai];
     float4 a[8];
     {
-        const float4* ap = rows_hat + (size_t)pa * (CSS_D / 4) + l8;
+        const float4* ap = rows + (size_t)pa * (CSS_D / 4) + l8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = __ldg(ap + i * 8);
     }
+    const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);       // cosine_similarity eps (loss.py:146)
     const float4* pp = proto_hat + (size_t)c * (CSS_D / 4) + l8;
     const float scale2 = 1.4426950408889634f / temp;          // logits in base 2: z2 = cos * log2(e) / temp
 
@@ -236,13 +239,14 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel
     const int n_cand = Nn + 1;
     const int cnt = (n_cand - warp + SC_WARPS - 1) / SC_WARPS;
     for (int base = 0; base < cnt; base += 32) {
-        // one candidate row id per lane: -1 = prototype, -2 = past the end
+        // one candidate per lane: row id (-1 = prototype, -2 = past the end) and 1 / max(||row||, 1e-8)
         int my_row = -2;
+        float my_inv = 1.f;
         {
             const int n = base + lane;
             const int j = warp + SC_WARPS * n;
             if (j == 0) {
-                my_row = -1;
+                my_row = -1;                                   // proto_hat is already normalised
             } else if (n < cnt) {
                 int seg, within;
                 if (neg_idx) {
@@ -253,23 +257,57 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel
                     within = draw_negative(dk, k, q, j - 1, tb.cdf, tb.rot_off, seg);
                 }
                 my_row = valid_list[(size_t)tb.rot_cls[seg] * N + within];
+                my_inv = 1.f / fmaxf(norms[my_row], 1e-8f);
             }
         }
         const int steps = min(8, (cnt - base + 3) >> 2);
-#pragma unroll 1
-        for (int t = 0; t < steps; ++t) {
-            const int row = __shfl_sync(0xffffffffu, my_row, t * 4 + grp);
-            const float4* p = (row >= 0) ? rows_hat + (size_t)row * (CSS_D / 4) + l8 : pp;
-            float4 r[8];
+        if (PREFETCH) {
+            // software pipeline: the next candidate row is in flight while the current one is scored
+            float4 rn[8];
+            int row_n = __shfl_sync(0xffffffffu, my_row, grp);
+            {
+                const float4* p = (row_n >= 0) ? rows + (size_t)row_n * (CSS_D / 4) + l8 : pp;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
-            const float cosv = group_sum8(dot8(a, r));
-            const float z = cosv * scale2;
-            if (row == -1) {
-                z0 = z;
-                cos_pos = cosv;
+                for (int i = 0; i < 8; ++i) rn[i] = __ldg(p + i * 8);
             }
-            online_update<WANT_GRAD>(st, z, row != -2, r);
+#pragma unroll 1
+            for (int t = 0; t < steps; ++t) {
+                float4 r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = rn[i];
+                const int row = row_n;
+                const float inv = __shfl_sync(0xffffffffu, my_inv, t * 4 + grp);
+                row_n = __shfl_sync(0xffffffffu, my_row, ((t + 1) & 7) * 4 + grp);
+                if (t + 1 < steps) {
+                    const float4* p = (row_n >= 0) ? rows + (size_t)row_n * (CSS_D / 4) + l8 : pp;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rn[i] = __ldg(p + i * 8);
+                }
+                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                const float z = cosv * scale2;
+                if (row == -1) {
+                    z0 = z;
+                    cos_pos = cosv;
+                }
+                online_update<WANT_GRAD>(st, z, row != -2, inv, r);
+            }
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < steps; ++t) {
+                const int row = __shfl_sync(0xffffffffu, my_row, t * 4 + grp);
+                const float inv = __shfl_sync(0xffffffffu, my_inv, t * 4 + grp);
+                const float4* p = (row >= 0) ? rows + (size_t)row * (CSS_D / 4) + l8 : pp;
+                float4 r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
+                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                const float z = cosv * scale2;
+                if (row == -1) {
+                    z0 = z;
+                    cos_pos = cosv;
+                }
+                online_update<WANT_GRAD>(st, z, row != -2, inv, r);
+            }
         }
     }
 
@@ -327,7 +365,7 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel
         // dL/da = (sum_j g_j r_hat_j - (sum_j g_j cos_j) a_hat) / max(||a||, eps),  g_j = (pi_j - [j==0]) / (Q V temp)
         // with sum_j pi_j r_hat_j = acc / l and sum_j pi_j cos_j = a_hat . (acc / l)        
         const float inv_l = 1.f / l;
-        const float4* ap = rows_hat + (size_t)pa * (CSS_D / 4);
+        const float4* ap = rows + (size_t)pa * (CSS_D / 4);
         const float4* php = proto_hat + (size_t)c * (CSS_D / 4);
         float4 S[2], av[2], ph[2];
         float sdot = 0.f;
@@ -344,14 +382,14 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 6) score_ce_kernel
                 t.w = fmaf(v.w, sc[w2], t.w);
             }
             S[h2] = make_float4(t.x * inv_l, t.y * inv_l, t.z * inv_l, t.w * inv_l);
-            av[h2] = __ldg(ap + col);
+            av[h2] = __ldg(ap + col);                       // raw anchor -> a_hat
+            av[h2].x *= inv_na; av[h2].y *= inv_na; av[h2].z *= inv_na; av[h2].w *= inv_na;
             ph[h2] = __ldg(php + col);
             sdot += S[h2].x * av[h2].x + S[h2].y * av[h2].y + S[h2].z * av[h2].z + S[h2].w * av[h2].w;
         }
         sdot = warp_sum(sdot);
         const float scale = 1.f / ((float)Q * (float)V * temp);
         const float tt = (sdot - s_pos[1]) * scale;
-        const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);
         float4* g = grad_anchor + ((size_t)k * Q + q) * (CSS_D / 4);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -383,11 +421,11 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
     }
 }
 
-extern "C" int css_score_ce(const float* rows_hat, const float* norms, const float* proto_hat, const float* class_cdf,
+extern "C" int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
                             const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta, const int32_t* anchor_idx,
                             const int32_t* neg_idx, uint64_t seed, uint64_t offset, int N, int C, int D, int Q, int Nn, float temp,
                             float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream) {
-    CSS_CHECK_ARG(rows_hat && norms && proto_hat && class_cdf && valid_list && hard_list && meta && loss_kq && anchor_px && loss,
+    CSS_CHECK_ARG(rows && norms && proto_hat && class_cdf && valid_list && hard_list && meta && loss_kq && anchor_px && loss,
                   CSS_E_ARG, "css_score_ce: null pointer");
     CSS_CHECK_ARG((anchor_idx == nullptr) == (neg_idx == nullptr), CSS_E_ARG,
                   "css_score_ce: anchor_idx and neg_idx must be fed together");
@@ -397,11 +435,11 @@ extern "C" int css_score_ce(const float* rows_hat, const float* norms, const flo
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(Q, C);
     if (grad_anchor)
-        score_ce_kernel<true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows_hat, norms, (const float4*)proto_hat, class_cdf,
+        score_ce_kernel<true, false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                           temp, loss_kq, anchor_px, (float4*)grad_anchor);
     else
-        score_ce_kernel<false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows_hat, norms, (const float4*)proto_hat, class_cdf,
+        score_ce_kernel<false, true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
                                                            valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                            temp, loss_kq, anchor_px, nullptr);
     loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);

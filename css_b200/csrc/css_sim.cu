@@ -25,134 +25,215 @@ __global__ void __launch_bounds__(CSS_D) proto_prep_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: each thread streams the 256 channels of SM_PPT pixels straight from the NCHW map (a warp reads 128 contiguous
-// bytes per channel and pixel group), keeps SM_PPT x 4*NG class dots + the squared norms in registers, and reads the
-// pre-normalised prototypes as 128-bit shared-memory broadcasts that each feed SM_PPT x 4 FMAs (the register blocking
-// over pixels is what keeps the shared-memory pipe off the critical path).  Persistent CTAs loop over 256-pixel chunks.
-//   cos_c = (x . p_hat_c) / max(||x||, 1e-12)                                   (ddp_model.py:105-109)
-//   mode CSS_SIM_SOFTMAX: softmax_c(cos_c / temp)                               (ddp_model.py:154)
-// Algorithmic bytes / pixel: D*4 read + C*4 written.
+// K1 "rep pass": ONE streaming read of an NCHW representation map that produces any combination of
+//   (a) the similarity of every pixel's 256-vector against the class prototypes
+//         cos_c = (x . p_hat_c) / max(||x||, 1e-12)                             (ddp_model.py:105-109)
+//         mode CSS_SIM_SOFTMAX: softmax_c(cos_c / temp)                         (ddp_model.py:154)
+//   (b) the pixel-major copy rows[p][256] (raw values) + ||x_p||, from which the loss gathers 1 KB candidate rows and
+//       accumulates class sums (loss.py:85,102,111-112,142: permute + boolean gathers).
+// Algorithmic bytes / pixel: D*4 read (+ C*4 written) (+ D*4 + 4 written).  At 22 FMA per 4-byte element (a) sits on
+// the fp32 FMA ridge of the SM (measured: FMA-issue bound, not HBM bound), so the inner loop spends as few issue slots
+// as possible per element, and (b) rides along for free under the FMA time:
+//   * packed fp32x2 FMAs (FFMA2, sm_100): one instruction updates two class dots;
+//   * each lane owns SM_PPT pixels x half of the channels (SM_KS = 2 channel slices per warp), so one 128-bit shared
+//     memory read of 4 pre-normalised prototype values feeds SM_PPT x 2 FFMA2 and the per-thread channel loop is short
+//     enough to keep 32 independent 4-byte loads in flight per thread;
+//   * the 16 consecutive channels a lane holds per step are 64 contiguous bytes of its pixel's row: the transpose is
+//     four 128-bit stores straight from registers, no shared-memory staging;
+//   * the two channel slices are combined with one xor-shuffle per value (fixed order: deterministic).
+// A warp reads 2 x 64 contiguous bytes per (channel pair, pixel group); the 4 warps of a CTA cover adjacent pixels.
 // ---------------------------------------------------------------------------------------------------------------
-#define SM_THREADS 64
-#define SM_PPT 4
-#define SM_CHUNK (SM_THREADS * SM_PPT)
+#define SM_PPT 2
+#define SM_KS 2
+#define SM_U 16
+#define SM_WARPS 4
+#define SM_MINB 4
 
-template <int NG>
-__global__ void __launch_bounds__(SM_THREADS) sim_map_kernel(const float* __restrict__ rep, const float* __restrict__ scratch,
-                                                             int hw, int N, int C, int mode, float temp, float* __restrict__ out) {
-    __shared__ float4 sp[CSS_D * NG];
-    for (int i = threadIdx.x; i < CSS_D * NG; i += SM_THREADS) {
-        int d = i / NG, g = i - d * NG;
-        sp[i] = reinterpret_cast<const float4*>(scratch)[d * (CSS_CMAX / 4) + g];
+template <int NG, bool ROWS>
+__global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const float* __restrict__ rep, const float* __restrict__ scratch,
+                                                                         int hw, int N, int C, int mode, float temp,
+                                                                         float* __restrict__ out, float* __restrict__ rows,
+                                                                         float* __restrict__ norms) {
+    constexpr int DS = CSS_D / SM_KS;          // channels per slice
+    constexpr int PL = 32 / SM_KS;             // pixel lanes per warp
+    constexpr int WP = PL * SM_PPT;            // pixels per warp
+    constexpr int NGA = NG > 0 ? NG : 1;
+    constexpr int SL = DS * NGA + 1;           // float4 per slice (+1 skew: the slices land in different banks)
+    __shared__ float4 sp[NG > 0 ? SM_KS * SL : 1];
+    if (NG > 0) {
+        for (int i = threadIdx.x; i < CSS_D * NG; i += SM_WARPS * 32) {
+            const int d = i / NGA, g = i - d * NGA;
+            sp[(d / DS) * SL + (d % DS) * NGA + g] = reinterpret_cast<const float4*>(scratch)[d * (CSS_CMAX / 4) + g];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int n_chunks = (N + SM_CHUNK - 1) / SM_CHUNK;
-    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ks = lane / PL, psub = lane % PL;
+    const float4* myp = sp + (NG > 0 ? ks * SL : 0);
+    const int n_wchunks = (N + WP - 1) / WP;
+    for (int wc = blockIdx.x * SM_WARPS + warp; wc < n_wchunks; wc += gridDim.x * SM_WARPS) {
         const float* x[SM_PPT];
         int pix[SM_PPT];
 #pragma unroll
         for (int j = 0; j < SM_PPT; ++j) {
-            pix[j] = chunk * SM_CHUNK + j * SM_THREADS + threadIdx.x;
+            pix[j] = wc * WP + j * PL + psub;
             const int p = min(pix[j], N - 1);                    // out-of-range lanes re-read the last pixel, never write
             const int b = p / hw;
-            x[j] = rep + (size_t)b * CSS_D * hw + (p - b * hw);
+            x[j] = rep + ((size_t)b * CSS_D + ks * DS) * hw + (p - b * hw);
         }
-        float acc[SM_PPT][4 * NG];
+        float2 acc[SM_PPT][2 * NGA];
         float n2[SM_PPT];
 #pragma unroll
         for (int j = 0; j < SM_PPT; ++j) {
             n2[j] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4 * NG; ++i) acc[j][i] = 0.f;
+            for (int i = 0; i < 2 * NGA; ++i) acc[j][i] = make_float2(0.f, 0.f);
         }
-        constexpr int U = 8;
 #pragma unroll 1
-        for (int d0 = 0; d0 < CSS_D; d0 += U) {
-            float v[U][SM_PPT];
+        for (int d0 = 0; d0 < DS; d0 += SM_U) {
+            float v[SM_U][SM_PPT];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < SM_U; ++u)
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) v[u][j] = ldg_stream(x[j] + (size_t)(d0 + u) * hw);
+            if (ROWS) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+                for (int j = 0; j < SM_PPT; ++j) {
+                    if (pix[j] < N) {
+                        float4* r = reinterpret_cast<float4*>(rows + (size_t)pix[j] * CSS_D + ks * DS + d0);
+#pragma unroll
+                        for (int u = 0; u < SM_U; u += 4) r[u / 4] = make_float4(v[u][j], v[u + 1][j], v[u + 2][j], v[u + 3][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SM_U; ++u) {
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) n2[j] = fmaf(v[u][j], v[u][j], n2[j]);
+                if (NG > 0) {
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const float4 q = sp[(d0 + u) * NG + g];
+                    for (int g = 0; g < NG; ++g) {
+                        const float4 q = myp[(d0 + u) * NGA + g];
 #pragma unroll
-                    for (int j = 0; j < SM_PPT; ++j) {
-                        acc[j][4 * g + 0] = fmaf(v[u][j], q.x, acc[j][4 * g + 0]);
-                        acc[j][4 * g + 1] = fmaf(v[u][j], q.y, acc[j][4 * g + 1]);
-                        acc[j][4 * g + 2] = fmaf(v[u][j], q.z, acc[j][4 * g + 2]);
-                        acc[j][4 * g + 3] = fmaf(v[u][j], q.w, acc[j][4 * g + 3]);
+                        for (int j = 0; j < SM_PPT; ++j) {
+                            const float2 vv = make_float2(v[u][j], v[u][j]);
+                            acc[j][2 * g + 0] = __ffma2_rn(vv, make_float2(q.x, q.y), acc[j][2 * g + 0]);
+                            acc[j][2 * g + 1] = __ffma2_rn(vv, make_float2(q.z, q.w), acc[j][2 * g + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        // combine the channel slices
+#pragma unroll
+        for (int o = PL; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < SM_PPT; ++j) {
+                n2[j] += __shfl_xor_sync(0xffffffffu, n2[j], o);
+                if (NG > 0) {
+#pragma unroll
+                    for (int i = 0; i < 2 * NG; ++i) {
+                        acc[j][i].x += __shfl_xor_sync(0xffffffffu, acc[j][i].x, o);
+                        acc[j][i].y += __shfl_xor_sync(0xffffffffu, acc[j][i].y, o);
                     }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < SM_PPT; ++j) {
-            if (pix[j] >= N) continue;
-            const int b = pix[j] / hw, s = pix[j] - b * hw;
-            const float nrm = fmaxf(sqrtf(n2[j]), 1e-12f);
-            float* o = out + (size_t)b * C * hw + s;
-            if (mode == CSS_SIM_COS) {
+            if (pix[j] >= N || (j % SM_KS) != ks) continue;      // slice j % KS writes pixel j
+            const float nrm_raw = sqrtf(n2[j]);
+            if (ROWS) norms[pix[j]] = nrm_raw;
+            if (NG > 0) {
+                const int b = pix[j] / hw, s = pix[j] - b * hw;
+                const float inv = __frcp_rn(fmaxf(nrm_raw, 1e-12f));
+                float* o = out + (size_t)b * C * hw + s;
+                float val[4 * NGA];
+#pragma unroll
+                for (int i = 0; i < 2 * NG; ++i) {
+                    val[2 * i] = acc[j][i].x * inv;
+                    val[2 * i + 1] = acc[j][i].y * inv;
+                }
+                if (mode == CSS_SIM_SOFTMAX) {            // softmax_c(cos_c / temp), evaluated in base 2
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 4 * NG; ++c)
+                        if (c < C) m = fmaxf(m, val[c]);
+                    const float k2 = 1.4426950408889634f / temp;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4 * NG; ++c) {
+                        val[c] = (c < C) ? exp2f((val[c] - m) * k2) : 0.f;
+                        sum += val[c];
+                    }
+                    const float inv_sum = __frcp_rn(sum);
+#pragma unroll
+                    for (int c = 0; c < 4 * NG; ++c) val[c] *= inv_sum;
+                }
 #pragma unroll
                 for (int c = 0; c < 4 * NG; ++c)
-                    if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[j][c], nrm);
-            } else {
-                float m = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4 * NG; ++c) {
-                    acc[j][c] = __fdiv_rn(__fdiv_rn(acc[j][c], nrm), temp);
-                    if (c < C) m = fmaxf(m, acc[j][c]);
-                }
-                float sum = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4 * NG; ++c) {
-                    acc[j][c] = (c < C) ? expf(acc[j][c] - m) : 0.f;
-                    sum += acc[j][c];
-                }
-#pragma unroll
-                for (int c = 0; c < 4 * NG; ++c)
-                    if (c < C) o[(size_t)c * hw] = __fdiv_rn(acc[j][c], sum);
+                    if (c < C) o[(size_t)c * hw] = val[c];
             }
         }
     }
 }
 
-template <int NG>
-static void launch_sim(const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
-                       cudaStream_t st) {
-    const int n_chunks = (N + SM_CHUNK - 1) / SM_CHUNK;
-    const int grid = n_chunks < css_cached_sm_count() * 8 ? n_chunks : css_cached_sm_count() * 8;
-    sim_map_kernel<NG><<<grid, SM_THREADS, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out);
+template <int NG, bool ROWS>
+static void launch_rep_pass(const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
+                            float* rows, float* norms, cudaStream_t st) {
+    constexpr int WP = (32 / SM_KS) * SM_PPT;
+    const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
+    const int cap = css_cached_sm_count() * SM_MINB;
+    rep_pass_kernel<NG, ROWS><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out, rows,
+                                                                                        norms);
+}
+
+template <bool ROWS>
+static void dispatch_rep_pass(int ng, const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
+                              float* rows, float* norms, cudaStream_t st) {
+    switch (ng) {
+        case 1: launch_rep_pass<1, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 2: launch_rep_pass<2, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 3: launch_rep_pass<3, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 4: launch_rep_pass<4, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 5: launch_rep_pass<5, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 6: launch_rep_pass<6, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 7: launch_rep_pass<7, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        default: launch_rep_pass<8, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+    }
+}
+
+extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C, int D, int h,
+                            int w, int mode, float temp, float* sim_out, float* rows, float* norms, void* stream) {
+    const bool want_sim = sim_out != nullptr, want_rows = rows != nullptr;
+    CSS_CHECK_ARG(rep && (want_sim || want_rows), CSS_E_ARG, "css_rep_pass: null pointer / nothing to do");
+    CSS_CHECK_ARG(!want_sim || (prototypes && proto_scratch), CSS_E_ARG, "css_rep_pass: sim_out needs prototypes and proto_scratch");
+    CSS_CHECK_ARG(want_rows == (norms != nullptr), CSS_E_ARG, "css_rep_pass: rows and norms go together");
+    CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_rep_pass: non-positive size");
+    CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX, CSS_E_ARG, "css_rep_pass: bad mode %d", mode);
+    if (int e = css_check_dims(want_sim ? C : 1, D)) return e;
+    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32, CSS_E_DTYPE, "css_rep_pass: rep dtype %d not supported", rep_dtype);
+    CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_rep_pass: too many pixels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = h * w, N = B * hw;
+    const float* r = (const float*)rep;
+    int launches = 1;
+    if (want_sim) {
+        proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
+        ++launches;
+        if (want_rows) dispatch_rep_pass<true>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);
+        else dispatch_rep_pass<false>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);
+    } else {
+        launch_rep_pass<0, true>(r, nullptr, hw, N, C, mode, temp, nullptr, rows, norms, st);
+    }
+    CSS_CHECK_LAUNCH("css_rep_pass", launches);
+    return 0;
 }
 
 extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C,
                            int D, int h, int w, int mode, float temp, float* out, void* stream) {
     CSS_CHECK_ARG(rep && prototypes && proto_scratch && out, CSS_E_ARG, "css_sim_map: null pointer");
-    CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_sim_map: non-positive size");
-    CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX, CSS_E_ARG, "css_sim_map: bad mode %d", mode);
-    if (int e = css_check_dims(C, D)) return e;
-    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32, CSS_E_DTYPE, "css_sim_map: rep dtype %d not supported", rep_dtype);
-    CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_sim_map: too many pixels");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int hw = h * w, N = B * hw;
-    proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
-    const float* r = (const float*)rep;
-    switch ((C + 3) / 4) {
-        case 1: launch_sim<1>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 2: launch_sim<2>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 3: launch_sim<3>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 4: launch_sim<4>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 5: launch_sim<5>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 6: launch_sim<6>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        case 7: launch_sim<7>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-        default: launch_sim<8>(r, proto_scratch, hw, N, C, mode, temp, out, st); break;
-    }
-    CSS_CHECK_LAUNCH("css_sim_map", 2);
-    return 0;
+    return css_rep_pass(rep, rep_dtype, prototypes, proto_scratch, B, C, D, h, w, mode, temp, out, nullptr, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,125 +1,94 @@
-// Stage 4a: ONE streaming read of the NCHW representation map that produces
-//   (1) the per-class feature sums of this rank (all-reduce payload replacing the reference's 116 MB all_gather,
-//       generalframeworks/loss/loss.py:77,81,102),
-//   (2) ||x_p|| per pixel and the pixel-major copy x_p / max(||x_p||, 1e-8) that the scoring kernel gathers 1 KB rows
-//       from (loss.py:85,111-112,142,146: permute + boolean gathers + cosine_similarity's normalisation).
-// HBM-bound: algorithmic bytes / pixel = D*4 read + D*4 written + 4 (norm) + 4 (class set).
+// Stage 4a: per-class feature sums and counts of this rank from the pixel-major copy of the representation map: the
+// all-reduce payload that replaces the reference's 116 MB all_gather (generalframeworks/loss/loss.py:77,81,102).
+// HBM/L2-bound: algorithmic bytes / pixel = D*4 + 4 read (the rows were just written by the rep pass and are partly L2
+// resident).
 //
-// Layout: a persistent grid of css_stream_blocks() CTAs, each owning a contiguous run of 32-pixel tiles.  A tile is
-// staged through shared memory ([256 ch][33]) by coalesced 128 B channel-row reads; the transposed write-out gives every
-// thread one channel column, so class sums accumulate in registers along runs of equal class sets (segmentation maps are
-// blocky) and spill to a per-CTA [C][256] shared accumulator only when the set changes: no atomics, deterministic.
+// Layout: css_class_blocks(N) CTAs of 64 threads, each owning a contiguous run of pixels; thread t owns channels
+// 4t..4t+3 (one 128-bit load per row, 1 KB per CTA per pixel, 4 rows in flight).  Class sums accumulate in registers
+// along runs of equal class sets (segmentation maps are blocky) and spill to the CTA's own [C][256] slice of `partials`
+// only when the set changes; a second kernel adds the slices of the CTAs that touched a class in CTA order: no atomics,
+// bit-reproducible.
 #include "css_common.cuh"
 
-#define ST_PIX 32
-#define ST_PAD 33
-#define ST_THREADS 256
+#define CS_THREADS 64
+#define CS_PIX 64            // pixels per CTA (upper bound of a CTA's pixel run when the grid is not capped)
 
-extern "C" int css_stream_blocks(void) { return css_cached_sm_count() * 4; }
+extern "C" int css_class_blocks(int N) {
+    const int want = (N + CS_PIX - 1) / CS_PIX;
+    const int cap = css_cached_sm_count() * 32;
+    return want < cap ? want : cap;
+}
 
-__device__ __forceinline__ void flush_run(float* sums, uint32_t bits, float run, int d) {
+__device__ __forceinline__ void flush_run(float4* part, uint32_t bits, uint32_t& seen, const float4& run) {
     while (bits) {
         const int c = __ffs(bits) - 1;
         bits &= bits - 1;
-        sums[c * CSS_D + d] += run;
+        float4* dst = part + (size_t)c * (CSS_D / 4);
+        if ((seen >> c) & 1u) {
+            float4 o = *dst;
+            o.x += run.x; o.y += run.y; o.z += run.z; o.w += run.w;
+            *dst = o;
+        } else {
+            *dst = run;
+        }
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) stream_rep_kernel(const float* __restrict__ rep, const uint32_t* __restrict__ valid_bits,
-                                                                int C, int hw, int N, float* __restrict__ rows_hat,
-                                                                float* __restrict__ norms, float* __restrict__ partials,
+__global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ valid_bits,
+                                                                int C, int N, float4* __restrict__ partials,
                                                                 uint32_t* __restrict__ touched) {
-    extern __shared__ float smem[];
-    float* tile = smem;                                   // [256][33]
-    float* red = tile + CSS_D * ST_PAD;                   // [8][32] partial squared norms
-    float* inv = red + 8 * ST_PIX;                        // [32]
-    uint32_t* bits_s = reinterpret_cast<uint32_t*>(inv + ST_PIX);   // [32]
-    float* sums = reinterpret_cast<float*>(bits_s + ST_PIX);        // [C][256]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < C * CSS_D; i += ST_THREADS) sums[i] = 0.f;
-
-    const int n_tiles = (N + ST_PIX - 1) / ST_PIX;
-    const int t_begin = (int)(((long long)n_tiles * blockIdx.x) / gridDim.x);
-    const int t_end = (int)(((long long)n_tiles * (blockIdx.x + 1)) / gridDim.x);
-
-    float run = 0.f;
+    const int t = threadIdx.x;
+    const int p_begin = (int)(((long long)N * blockIdx.x) / gridDim.x);
+    const int p_end = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
+    float4* part = partials + (size_t)blockIdx.x * C * (CSS_D / 4) + t;
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t run_bits = 0, seen = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-        const int p0 = t * ST_PIX;
-        // ---- load: warp w reads channels [32w, 32w+32), lane = pixel; 32 independent 128 B rows in flight per warp
-        {
-            const int p = p0 + lane;
-            const bool ok = p < N;
-            const int b = ok ? p / hw : 0, s = ok ? p - b * hw : 0;
-            const float* x = rep + ((size_t)b * CSS_D + warp * 32) * hw + s;
-            float v[32];
+    for (int p0 = p_begin; p0 < p_end; p0 += 4) {
+        float4 v[4];
+        uint32_t b[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ok ? ldg_stream(x + (size_t)i * hw) : 0.f;
-            float n2 = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = p0 + i < p_end;
+            b[i] = ok ? __ldg(valid_bits + p0 + i) : 0u;
+            v[i] = (ok && b[i]) ? ldg_stream4(rows + (size_t)(p0 + i) * (CSS_D / 4) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                tile[(warp * 32 + i) * ST_PAD + lane] = v[i];
-                n2 = fmaf(v[i], v[i], n2);
+        for (int i = 0; i < 4; ++i) {
+            if (b[i] != run_bits) {                          // CTA-uniform branch
+                const uint32_t rb = run_bits;
+                flush_run(part, rb, seen, run);
+                seen |= rb;
+                run = make_float4(0.f, 0.f, 0.f, 0.f);
+                run_bits = b[i];
             }
-            red[warp * ST_PIX + lane] = n2;
-            if (warp == 0) bits_s[lane] = ok ? valid_bits[p] : 0u;
+            run.x += v[i].x; run.y += v[i].y; run.z += v[i].z; run.w += v[i].w;
         }
-        __syncthreads();
-        if (warp == 0) {
-            float n2 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) n2 += red[k * ST_PIX + lane];
-            const float nrm = sqrtf(n2);
-            inv[lane] = 1.f / fmaxf(nrm, 1e-8f);           // cosine_similarity eps (loss.py:146)
-            if (p0 + lane < N) norms[p0 + lane] = nrm;
-        }
-        __syncthreads();
-        // ---- transposed write-out + class sums: thread = channel d, loop over the tile's pixels
-        {
-            const int d = tid;
-            const int n_here = min(ST_PIX, N - p0);
-            float* out = rows_hat + (size_t)p0 * CSS_D + d;
-#pragma unroll 8
-            for (int i = 0; i < n_here; ++i) {
-                const float v = tile[d * ST_PAD + i];
-                out[(size_t)i * CSS_D] = v * inv[i];
-                const uint32_t bits = bits_s[i];
-                if (bits != run_bits) {                     // block-uniform branch
-                    flush_run(sums, run_bits, run, d);
-                    seen |= run_bits;
-                    run = 0.f;
-                    run_bits = bits;
-                }
-                run += v;
-            }
-        }
-        __syncthreads();
     }
-    flush_run(sums, run_bits, run, tid);
-    seen |= run_bits;
-    // per-CTA partial sums of the classes this CTA touched (thread d only ever touched sums[*][d]: no sync needed)
-    for (uint32_t u = seen; u;) {
-        const int c = __ffs(u) - 1;
-        u &= u - 1;
-        partials[((size_t)blockIdx.x * C + c) * CSS_D + tid] = sums[c * CSS_D + tid];
+    {
+        const uint32_t rb = run_bits;
+        flush_run(part, rb, seen, run);
+        seen |= rb;
     }
-    if (tid == 0) touched[blockIdx.x] = seen;
+    if (t == 0) touched[blockIdx.x] = seen;
 }
 
-// deterministic second stage: block c first compacts the ids of the CTAs that touched class c (ballot order = CTA order),
-// then thread d adds their partials 8 loads at a time, always in the same order.
-__global__ void __launch_bounds__(CSS_D) stream_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
-                                                              const int32_t* __restrict__ meta, int G, int C,
-                                                              float* __restrict__ class_stats) {
+// deterministic second stage: block c first compacts the ids of the CTAs that touched class c (ballot order = CTA order);
+// the list is cut into CR_SEG contiguous segments, thread (seg, d) adds its segment's partials 8 loads at a time, and
+// the segment sums are combined in segment order: always the same association, whatever the timing.
+#define CR_SEG 4
+__global__ void __launch_bounds__(CSS_D * CR_SEG) class_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
+                                                                      const int32_t* __restrict__ meta, int G, int C,
+                                                                      float* __restrict__ class_stats) {
     extern __shared__ int glist[];                 // [G]
-    __shared__ int wtot[CSS_D / 32];
+    __shared__ int wtot[CSS_D * CR_SEG / 32];
+    __shared__ float segsum[CR_SEG][CSS_D];
     __shared__ int n_list;
-    const int c = blockIdx.x, d = threadIdx.x, warp = d >> 5, lane = d & 31;
-    if (d == 0) n_list = 0;
+    constexpr int NT = CSS_D * CR_SEG, NW = NT / 32;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) n_list = 0;
     __syncthreads();
-    for (int base = 0; base < G; base += CSS_D) {
-        const int g = base + d;
+    for (int base = 0; base < G; base += NT) {
+        const int g = base + tid;
         const bool on = g < G && ((touched[g] >> c) & 1u);
         const uint32_t bal = __ballot_sync(0xffffffffu, on);
         if (lane == 0) wtot[warp] = __popc(bal);
@@ -128,47 +97,47 @@ __global__ void __launch_bounds__(CSS_D) stream_reduce_kernel(const float* __res
         for (int w2 = 0; w2 < warp; ++w2) off += wtot[w2];
         if (on) glist[off + __popc(bal & ((1u << lane) - 1u))] = g;
         __syncthreads();
-        if (d == 0) {
-            int t = 0;
-            for (int w2 = 0; w2 < CSS_D / 32; ++w2) t += wtot[w2];
-            n_list += t;
+        if (tid == 0) {
+            int tt = 0;
+            for (int w2 = 0; w2 < NW; ++w2) tt += wtot[w2];
+            n_list += tt;
         }
         __syncthreads();
     }
     const int n = n_list;
+    const int seg = tid / CSS_D, d = tid - seg * CSS_D;
+    const int per = (n + CR_SEG - 1) / CR_SEG;
+    const int i0 = min(seg * per, n), i1 = min(i0 + per, n);
     float acc = 0.f;
-    int i = 0;
-    for (; i + 8 <= n; i += 8) {
+    int i = i0;
+    for (; i + 8 <= i1; i += 8) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = partials[((size_t)glist[i + u] * C + c) * CSS_D + d];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += v[u];
     }
-    for (; i < n; ++i) acc += partials[((size_t)glist[i] * C + c) * CSS_D + d];
-    class_stats[c * (CSS_D + 1) + d] = acc;
-    if (d == 0) class_stats[c * (CSS_D + 1) + CSS_D] = (float)meta[CSS_META_N_VALID + c];
+    for (; i < i1; ++i) acc += partials[((size_t)glist[i] * C + c) * CSS_D + d];
+    segsum[seg][d] = acc;
+    __syncthreads();
+    if (seg == 0) {
+        float tot = segsum[0][d];
+#pragma unroll
+        for (int s2 = 1; s2 < CR_SEG; ++s2) tot += segsum[s2][d];
+        class_stats[c * (CSS_D + 1) + d] = tot;
+        if (d == 0) class_stats[c * (CSS_D + 1) + CSS_D] = (float)meta[CSS_META_N_VALID + c];
+    }
 }
 
-extern "C" int css_stream_rep(const void* rep, int rep_dtype, const uint32_t* valid_bits, const int32_t* meta, int B2, int C,
-                              int D, int h, int w, float* rows_hat, float* norms, float* partials, uint32_t* touched,
-                              float* class_stats, void* stream) {
-    CSS_CHECK_ARG(rep && valid_bits && meta && rows_hat && norms && partials && touched && class_stats, CSS_E_ARG,
-                  "css_stream_rep: null pointer");
-    CSS_CHECK_ARG(B2 > 0 && h > 0 && w > 0, CSS_E_ARG, "css_stream_rep: non-positive size");
+extern "C" int css_class_stats(const float* rows, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
+                               float* partials, uint32_t* touched, float* class_stats, void* stream) {
+    CSS_CHECK_ARG(rows && valid_bits && meta && partials && touched && class_stats, CSS_E_ARG, "css_class_stats: null pointer");
+    CSS_CHECK_ARG(N > 0, CSS_E_ARG, "css_class_stats: non-positive size");
     if (int e = css_check_dims(C, D)) return e;
-    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32, CSS_E_DTYPE, "css_stream_rep: rep dtype %d not supported", rep_dtype);
-    CSS_CHECK_ARG((long long)B2 * h * w * CSS_CMAX < (1ll << 31), CSS_E_SIZE, "css_stream_rep: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
-    const int hw = h * w, N = B2 * hw, G = css_stream_blocks();
-    const size_t smem = (size_t)(CSS_D * ST_PAD + 8 * ST_PIX + 2 * ST_PIX + C * CSS_D) * sizeof(float);
-    {   // > 48 KB of dynamic shared memory needs the opt-in (host-side attribute, legal during graph capture)
-        cudaError_t e = cudaFuncSetAttribute(stream_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)((CSS_D * ST_PAD + 10 * ST_PIX + CSS_CMAX * CSS_D) * sizeof(float)));
-        if (e != cudaSuccess) { css_set_error("css_stream_rep: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    }
-    stream_rep_kernel<<<G, ST_THREADS, smem, st>>>((const float*)rep, valid_bits, C, hw, N, rows_hat, norms, partials, touched);
-    stream_reduce_kernel<<<C, CSS_D, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
-    CSS_CHECK_LAUNCH("css_stream_rep", 2);
+    const int G = css_class_blocks(N);
+    class_sums_kernel<<<G, CS_THREADS, 0, st>>>((const float4*)rows, valid_bits, C, N, (float4*)partials, touched);
+    class_reduce_kernel<<<C, CSS_D * CR_SEG, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
+    CSS_CHECK_LAUNCH("css_class_stats", 2);
     return 0;
 }

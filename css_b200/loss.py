@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .ops import _cuda_f32
+from .ops import _cuda_f32, rep_rows, rows_key
 
 
 class _Workspace:
@@ -25,7 +25,7 @@ class _Workspace:
         N = B2 * h * w
         T = lib.css_select_tiles(N)
         with torch.cuda.device(device):
-            G = lib.css_stream_blocks()
+            G = lib.css_class_blocks(N)
         i32 = dict(device=device, dtype=torch.int32)
         f32 = dict(device=device, dtype=torch.float32)
         self.key = (B2, C, D, h, w, Q, Nn, str(device))
@@ -36,8 +36,6 @@ class _Workspace:
         self.valid_list = torch.empty(C * N, **i32)
         self.hard_list = torch.empty(C * N, **i32)
         self.meta = torch.zeros(_lib.META_WORDS, **i32)
-        self.rows_hat = torch.empty(N * D, **f32)
-        self.norms = torch.empty(N, **f32)
         self.partials = torch.empty(G * C * D, **f32)
         self.touched = torch.empty(G, **i32)
         self.class_stats = torch.empty(C, D + 1, **f32)
@@ -57,7 +55,7 @@ def allreduce_class_stats(class_stats, group=None):
 
 class _ContrastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rep, label, mask, prob, prototypes, mod, indices, want_grad):
+    def forward(ctx, rep, label, mask, prob, prototypes, mod, indices, want_grad, cache):
         lib = _lib.load()
         B2, D, h, w = rep.shape
         C = label.shape[1]
@@ -69,8 +67,12 @@ class _ContrastFn(torch.autograd.Function):
         check(lib.css_select(ptr(label), ptr(mask), ptr(prob), float(mod.strong_threshold), B2, C, h, w, ptr(ws.valid_bits),
                              ptr(ws.hard_bits), ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), st),
               "css_select")
-        check(lib.css_stream_rep(ptr(rep), _lib.DTYPE_F32, ptr(ws.valid_bits), ptr(ws.meta), B2, C, D, h, w, ptr(ws.rows_hat),
-                                 ptr(ws.norms), ptr(ws.partials), ptr(ws.touched), ptr(ws.class_stats), st), "css_stream_rep")
+        if cache is not None and cache.key == rows_key(rep):      # rows written by the same read that produced `prob`
+            rows, norms = cache.rows, cache.norms
+        else:
+            rows, norms = rep_rows(rep)
+        check(lib.css_class_stats(ptr(rows), ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
+                                  ptr(ws.class_stats), st), "css_class_stats")
         allreduce_class_stats(ws.class_stats, mod.process_group)
         check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
                                 float(mod.temp), C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
@@ -86,7 +88,7 @@ class _ContrastFn(torch.autograd.Function):
         if ev is not None:                       # bench.py times the dominant kernel live, on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.css_score_ce(ptr(ws.rows_hat), ptr(ws.norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+        check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
                                ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, N, C, D, Q, Nn,
                                float(mod.temp), ptr(ws.loss_kq), ptr(anchor_px), ptr(grad_anchor), ptr(loss), st), "css_score_ce")
         if ev is not None:
@@ -95,7 +97,8 @@ class _ContrastFn(torch.autograd.Function):
         ctx.shape = (B2, D, h, w)
         ctx.n_anchor = C * Q
         ctx.save_for_backward(anchor_px, grad_anchor)
-        mod.last = dict(ws=ws, anchor_px=anchor_px, grad_anchor=grad_anchor, seed=seed, offset=offset)
+        mod.last = dict(ws=ws, anchor_px=anchor_px, grad_anchor=grad_anchor, seed=seed, offset=offset, rows=rows, norms=norms,
+                        rows_from_cache=cache is not None and cache.key == rows_key(rep))
         return loss
 
     @staticmethod
@@ -110,7 +113,7 @@ class _ContrastFn(torch.autograd.Function):
         with torch.cuda.device(anchor_px.device):
             check(lib.css_grad_scatter(ptr(go), ptr(anchor_px), ptr(grad_anchor), ctx.n_anchor, B2, D, h, w, ptr(grad_rep),
                                        stream_ptr()), "css_grad_scatter")
-        return grad_rep, None, None, None, None, None, None, None
+        return grad_rep, None, None, None, None, None, None, None, None
 
 
 class Contrast_Loss(nn.Module):
@@ -173,8 +176,9 @@ class Contrast_Loss(nn.Module):
             if not (a.is_cuda and n.is_cuda and a.dtype == torch.int32 and n.dtype == torch.int32):
                 raise RuntimeError("css_b200: _indices must be int32 CUDA tensors")
             _indices = (a.contiguous(), n.contiguous())
+        cache = getattr(prob, "_css_rows", None)
         with torch.cuda.device(rep.device):
-            return _ContrastFn.apply(rep_c, label_c, mask_c, prob_c, prototypes.detach(), self, _indices, want_grad)
+            return _ContrastFn.apply(rep_c, label_c, mask_c, prob_c, prototypes.detach(), self, _indices, want_grad, cache)
 
     # ---- verification helpers (read device state back: they synchronise, never used on the training path) --------------
     def selection(self):

@@ -28,13 +28,42 @@ def cos_sim_map(rep, prototypes):
     return _sim(rep, prototypes, _lib.SIM_COS, 1.0)
 
 
-def proto_softmax_sim(rep_all, prototypes, temp):
+def proto_softmax_sim(rep_all, prototypes, temp, with_rows=True):
     """prob_all = softmax(cos(rep_all, prototypes) / temp) at rep resolution (the hard-anchor indicator).
-    Replaces ddp_model.py:147-154 (Model_mix) / :230-237 (Model_cross)."""
-    return _sim(rep_all, prototypes, _lib.SIM_SOFTMAX, float(temp))
+    Replaces ddp_model.py:147-154 (Model_mix) / :230-237 (Model_cross).
+
+    The same single read of rep_all also writes the pixel-major copy + norms the contrastive loss needs; they ride on
+    the returned tensor (`prob._css_rows`) so that Contrast_Loss.forward(rep_all, ..., prob, ...) does not read rep_all
+    a second time.  Purely an optimisation: the loss re-derives them whenever the attachment does not match its `rep`."""
+    return _sim(rep_all, prototypes, _lib.SIM_SOFTMAX, float(temp), with_rows)
 
 
-def _sim(rep, prototypes, mode, temp):
+class RowsCache:
+    """Pixel-major copy of one representation map, tagged with what it was derived from."""
+
+    def __init__(self, rep, rows, norms):
+        self.key = rows_key(rep)
+        self.rows, self.norms = rows, norms
+
+
+def rows_key(rep):
+    return (rep.data_ptr(), tuple(rep.shape), rep._version, str(rep.device))
+
+
+def rep_rows(rep):
+    """Pixel-major copy rows [N,256] + norms [N] of an NCHW representation map (one streaming read)."""
+    rep = _cuda_f32(rep, "rep")
+    B, D, h, w = rep.shape
+    rows = torch.empty((B * h * w, D), device=rep.device, dtype=torch.float32)
+    norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(rep.device):
+        check(lib.css_rep_pass(ptr(rep), _lib.DTYPE_F32, None, None, B, 1, D, h, w, _lib.SIM_COS, 1.0, None, ptr(rows), ptr(norms),
+                               stream_ptr()), "css_rep_pass")
+    return rows, norms
+
+
+def _sim(rep, prototypes, mode, temp, with_rows=False):
     rep = _cuda_f32(rep, "rep")
     prototypes = _cuda_f32(prototypes, "prototypes")
     B, D, h, w = rep.shape
@@ -43,10 +72,16 @@ def _sim(rep, prototypes, mode, temp):
         raise RuntimeError("css_b200: prototypes must be [C, D]")
     out = torch.empty((B, C, h, w), device=rep.device, dtype=torch.float32)
     scratch = _proto_scratch(rep.device)
+    rows = norms = None
+    if with_rows:
+        rows = torch.empty((B * h * w, D), device=rep.device, dtype=torch.float32)
+        norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
-        check(lib.css_sim_map(ptr(rep), _lib.DTYPE_F32, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
-                              stream_ptr()), "css_sim_map")
+        check(lib.css_rep_pass(ptr(rep), _lib.DTYPE_F32, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
+                               ptr(rows), ptr(norms), stream_ptr()), "css_rep_pass")
+    if with_rows:
+        out._css_rows = RowsCache(rep, rows, norms)
     return out
 
 

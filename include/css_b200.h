@@ -62,13 +62,19 @@ int         css_sm_count(void);
 /* cumulative number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long css_launch_count(void);
 
-/* ---- stage 1 / 1b --------------------------------------------------------------------------------------------
- * Cosine (mode CSS_SIM_COS) or softmax (CSS_SIM_SOFTMAX) similarity of every pixel's D-vector against the class
- * prototypes.  Replaces ddp_model.py:104-110 (teacher sim_mat), :147-154 / :230-237 (student prob_all).
- *   rep        [B, D, h, w]  rep_dtype            prototypes [C, D] f32
- *   proto_scratch  f32[D * 32]  scratch (normalised, transposed prototypes; F.normalize eps 1e-12)
- *   out        [B, C, h, w] f32
+/* ---- stage 1 / 1b (+ the loss's pixel-major copy): ONE streaming read of an NCHW representation map -----------------
+ * css_rep_pass produces any combination of
+ *  (a) sim_out [B,C,h,w] f32: cosine (mode CSS_SIM_COS) or softmax_c(cos/temp) (CSS_SIM_SOFTMAX) similarity of every
+ *      pixel's D-vector against the class prototypes.  Replaces ddp_model.py:104-110 (teacher sim_mat) and
+ *      :147-154 / :230-237 (student prob_all).  Needs prototypes [C,D] and proto_scratch f32[D*32] (normalised,
+ *      transposed prototypes; F.normalize eps 1e-12).
+ *  (b) rows f32[N*D] + norms f32[N]: the pixel-major copy (row p = pixel id p, raw values) and ||x_p||, from which the
+ *      loss gathers candidate rows and accumulates class sums (loss.py:85,102,111-112,142).
+ * NULL sim_out skips (a); NULL rows/norms skips (b).  css_sim_map is (a) alone.
  */
+int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
+                 int B, int C, int D, int h, int w, int mode, float temp,
+                 float* sim_out, float* rows, float* norms, void* stream);
 int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                 int B, int C, int D, int h, int w, int mode, float temp, float* out, void* stream);
 
@@ -100,20 +106,16 @@ int css_select(const float* label, const float* mask, const float* prob, float s
                uint32_t* valid_bits, uint32_t* hard_bits, int32_t* tile_counts,
                int32_t* valid_list, int32_t* hard_list, int32_t* meta, void* stream);
 
-/* ---- stage 4a: one streaming read of rep -------------------------------------------------------------------------
- * Per-class feature sums and counts of this rank (the all-reduce payload that replaces the reference's all_gather,
- * loss.py:77,81,102) and the pixel-major normalised copy the scoring kernel gathers from.
- *   rep [B2,D,h,w] rep_dtype, valid_bits u32[N], meta i32[CSS_META_WORDS] (from css_select: the local counts)
- *   rows_hat  f32[N*D]   x_p / max(||x_p||, 1e-8), pixel-major (row p = pixel id p)
- *   norms     f32[N]     ||x_p||
- *   partials  f32[css_stream_blocks() * (C*D)] + touched u32[css_stream_blocks()]  scratch (deterministic reduce)
+/* ---- stage 4a: per-class statistics ----------------------------------------------------------------------------------
+ * Per-class feature sums and counts of this rank from the pixel-major rows: the all-reduce payload that replaces the
+ * reference's all_gather (loss.py:77,81,102).  Deterministic (no atomics).
+ *   rows f32[N*D] (from css_rep_pass), valid_bits u32[N], meta i32[CSS_META_WORDS] (from css_select: the local counts)
+ *   partials  f32[css_class_blocks(N) * C * D] + touched u32[css_class_blocks(N)]   scratch
  *   class_stats f32[C*(D+1)]  row c = [sum_d ... , count]
  */
-int css_stream_blocks(void);
-int css_stream_rep(const void* rep, int rep_dtype, const uint32_t* valid_bits, const int32_t* meta,
-                   int B2, int C, int D, int h, int w,
-                   float* rows_hat, float* norms, float* partials, uint32_t* touched, float* class_stats,
-                   void* stream);
+int css_class_blocks(int N);
+int css_class_stats(const float* rows, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
+                    float* partials, uint32_t* touched, float* class_stats, void* stream);
 
 /* ---- stage 4b: prototype EMA --------------------------------------------------------------------------------------
  * For every class present on THIS rank: mean = global_sum / global_count; prototypes[c] = mean if sum(prototypes[c])==0
@@ -137,13 +139,13 @@ int css_sample(const int32_t* meta, const float* class_cdf, uint64_t seed, uint6
                int32_t* anchor_idx, int32_t* neg_idx, void* stream);
 
 /* ---- stage 3: scoring + cross-entropy + d loss / d anchor ------------------------------------------------------------
- * Replaces loss.py:124-149 and its autograd backward up to the anchor rows.
+ * Replaces loss.py:124-149 and its autograd backward up to the anchor rows.  rows / norms come from css_rep_pass.
  *   anchor_idx / neg_idx: as produced by css_sample or recorded from the reference; NULL = draw on the fly with
  *   (seed, offset), bit-identical to css_sample with the same arguments.
  *   loss_kq f32[C*Q], anchor_px i32[C*Q] (pixel id of each anchor, -1 if none), grad_anchor f32[C*Q*D] or NULL,
  *   loss f32[1] = (1/V) sum_k (1/Q) sum_q loss_kq, exactly 0 when V <= 1.
  */
-int css_score_ce(const float* rows_hat, const float* norms, const float* proto_hat, const float* class_cdf,
+int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
                  const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta,
                  const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset,
                  int N, int C, int D, int Q, int Nn, float temp,

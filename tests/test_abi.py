@@ -21,7 +21,7 @@ def header_functions():
 
 def test_header_declares_the_path():
     fns = header_functions()
-    for name in ["css_sim_map", "css_upsample_label_fuse", "css_select", "css_stream_rep", "css_proto_ema", "css_sample",
+    for name in ["css_sim_map", "css_upsample_label_fuse", "css_select", "css_rep_pass", "css_class_stats", "css_proto_ema", "css_sample",
                  "css_score_ce", "css_grad_scatter", "css_threshold_glue", "css_version", "css_last_error"]:
         assert name in fns
 

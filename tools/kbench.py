@@ -70,9 +70,11 @@ def main():
         check(lib.css_select(ptr(label), ptr(mask), ptr(prob), float(cfg["strong"]), B2, C, h, w, ptr(ws.valid_bits), ptr(ws.hard_bits),
                              ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), stream_ptr()), "select")
 
+    rows, norms = crit.last["rows"], crit.last["norms"]
+
     def stream(i):
-        check(lib.css_stream_rep(ptr(rep_all[i % P]), 0, ptr(ws.valid_bits), ptr(ws.meta), B2, C, D, h, w, ptr(ws.rows_hat),
-                                 ptr(ws.norms), ptr(ws.partials), ptr(ws.touched), ptr(ws.class_stats), stream_ptr()), "stream")
+        check(lib.css_class_stats(ptr(rows), ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
+                                  ptr(ws.class_stats), stream_ptr()), "class_stats")
 
     p2 = protos.clone()
 
@@ -85,7 +87,7 @@ def main():
     loss = torch.empty((), device=dev)
 
     def score(i, grad=True):
-        check(lib.css_score_ce(ptr(ws.rows_hat), ptr(ws.norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+        check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
                                ptr(ws.hard_list), ptr(ws.meta), None, None, 7, i, N, C, D, Q, Nn, temp, ptr(ws.loss_kq),
                                ptr(anchor_px), ptr(grad_anchor) if grad else None, ptr(loss), stream_ptr()), "score")
 
@@ -96,12 +98,13 @@ def main():
         check(lib.css_grad_scatter(ptr(one), ptr(anchor_px), ptr(grad_anchor), C * Q, B2, D, h, w, ptr(grads[i % P]), stream_ptr()), "scatter")
 
     res["select (3 kernels)"] = timeit(select, a.iters)
-    res["stream_rep (+reduce)"] = timeit(stream, a.iters)
+    res["class_stats (+reduce)"] = timeit(stream, a.iters)
+    res["rep_rows only (ori flow)"] = timeit(lambda i: css_b200.ops.rep_rows(rep_all[i % P]), a.iters)
     res["proto_ema (+cdf)"] = timeit(ema, a.iters)
     res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
     res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
     res["grad_scatter (+memset)"] = timeit(scatter, a.iters)
-    tot = sum(v for k, v in res.items() if k != "score_ce fwd only")
+    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)"))
     for k, v in res.items():
         print(f"{k:34s} {v:9.1f} us")
     print(f"{'sum (path)':34s} {tot:9.1f} us")
