@@ -190,6 +190,116 @@ __device__ __forceinline__ void online_update(Online& st, float z, bool valid, f
     }
 }
 
+struct QueryShared {                     // per-CTA scratch for merging the SC_WARPS warp states
+    float4 acc[SC_WARPS][CSS_D / 4];
+    float m[SC_WARPS], l[SC_WARPS], pos[2];
+};
+
+// Merge the four 8-lane groups of every warp, then the SC_WARPS warps (fixed order), and write the query's loss, anchor
+// pixel and d loss / d anchor.
+template <bool WANT_GRAD>
+__device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos, QueryShared& sh, const float4* __restrict__ rows,
+                                             const float4* __restrict__ proto_hat, float inv_na, int pa, int c, int k, int q, int Q,
+                                             int V, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
+                                             float4* __restrict__ grad_anchor) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, l8 = lane & 7;
+    float4 (&s_acc)[SC_WARPS][CSS_D / 4] = sh.acc;
+    float (&s_m)[SC_WARPS] = sh.m;
+    float (&s_l)[SC_WARPS] = sh.l;
+    float (&s_pos)[2] = sh.pos;
+    // merge the four groups (xor 8, xor 16); afterwards every lane holds the warp's state for its column slice
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float m_o = __shfl_xor_sync(0xffffffffu, st.m, o);
+        const float l_o = __shfl_xor_sync(0xffffffffu, st.l, o);
+        const float M = fmaxf(st.m, m_o);
+        const float s_a = (st.m == -INFINITY) ? 0.f : exp2f(st.m - M);
+        const float s_b = (m_o == -INFINITY) ? 0.f : exp2f(m_o - M);
+        st.l = st.l * s_a + l_o * s_b;
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                st.acc[i].x = st.acc[i].x * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].x, o) * s_b;
+                st.acc[i].y = st.acc[i].y * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].y, o) * s_b;
+                st.acc[i].z = st.acc[i].z * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].z, o) * s_b;
+                st.acc[i].w = st.acc[i].w * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].w, o) * s_b;
+            }
+        }
+        st.m = M;
+    }
+    if (lane == 0) {
+        s_m[warp] = st.m;
+        s_l[warp] = st.l;
+        if (warp == 0) {
+            s_pos[0] = z0;
+            s_pos[1] = cos_pos;
+        }
+    }
+    if (WANT_GRAD && grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_acc[warp][i * 8 + l8] = st.acc[i];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+
+    // warp 0 merges the SC_WARPS warp states in warp order
+    float M = s_m[0];
+#pragma unroll
+    for (int w2 = 1; w2 < SC_WARPS; ++w2) M = fmaxf(M, s_m[w2]);
+    float sc[SC_WARPS], l = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < SC_WARPS; ++w2) {
+        sc[w2] = (s_m[w2] == -INFINITY) ? 0.f : exp2f(s_m[w2] - M);
+        l += s_l[w2] * sc[w2];
+    }
+    // CE with target 0: logsumexp(z) - z_0 (loss.py:147), evaluated in base 2
+    if (lane == 0) {
+        loss_kq[k * Q + q] = 0.6931471805599453f * ((M + log2f(l)) - s_pos[0]);
+        anchor_px[k * Q + q] = pa;
+    }
+    if (WANT_GRAD) {
+        // dL/da = (sum_j g_j r_hat_j - (sum_j g_j cos_j) a_hat) / max(||a||, eps),  g_j = (pi_j - [j==0]) / (Q V temp)
+        // with sum_j pi_j r_hat_j = acc / l and sum_j pi_j cos_j = a_hat . (acc / l)        (SURVEY.md Appendix A.4)
+        const float inv_l = 1.f / l;
+        const float4* ap = rows + (size_t)pa * (CSS_D / 4);
+        const float4* php = proto_hat + (size_t)c * (CSS_D / 4);
+        float4 S[2], av[2], ph[2];
+        float sdot = 0.f;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int col = lane + 32 * h2;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w2 = 0; w2 < SC_WARPS; ++w2) {
+                const float4 v = s_acc[w2][col];
+                t.x = fmaf(v.x, sc[w2], t.x);
+                t.y = fmaf(v.y, sc[w2], t.y);
+                t.z = fmaf(v.z, sc[w2], t.z);
+                t.w = fmaf(v.w, sc[w2], t.w);
+            }
+            S[h2] = make_float4(t.x * inv_l, t.y * inv_l, t.z * inv_l, t.w * inv_l);
+            av[h2] = __ldg(ap + col);                       // raw anchor -> a_hat
+            av[h2].x *= inv_na; av[h2].y *= inv_na; av[h2].z *= inv_na; av[h2].w *= inv_na;
+            ph[h2] = __ldg(php + col);
+            sdot += S[h2].x * av[h2].x + S[h2].y * av[h2].y + S[h2].z * av[h2].z + S[h2].w * av[h2].w;
+        }
+        sdot = warp_sum(sdot);
+        const float scale = 1.f / ((float)Q * (float)V * temp);
+        const float tt = (sdot - s_pos[1]) * scale;
+        float4* g = grad_anchor + ((size_t)k * Q + q) * (CSS_D / 4);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            float4 o;
+            o.x = ((S[h2].x - ph[h2].x) * scale - tt * av[h2].x) * inv_na;
+            o.y = ((S[h2].y - ph[h2].y) * scale - tt * av[h2].y) * inv_na;
+            o.z = ((S[h2].z - ph[h2].z) * scale - tt * av[h2].z) * inv_na;
+            o.w = ((S[h2].w - ph[h2].w) * scale - tt * av[h2].w) * inv_na;
+            g[lane + 32 * h2] = o;
+        }
+    }
+}
+
 template <bool WANT_GRAD, bool PREFETCH>
 __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel(
     const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
@@ -198,8 +308,7 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel
     uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
     float4* __restrict__ grad_anchor) {
     __shared__ SlotTables tb;
-    __shared__ float4 s_acc[SC_WARPS][CSS_D / 4];
-    __shared__ float s_m[SC_WARPS], s_l[SC_WARPS], s_pos[2];
+    __shared__ QueryShared sh;
     const int k = blockIdx.y, q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int V = meta[CSS_META_V];
@@ -311,96 +420,7 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel
         }
     }
 
-    // merge the four groups (xor 8, xor 16); afterwards every lane holds the warp's state for its column slice
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-        const float m_o = __shfl_xor_sync(0xffffffffu, st.m, o);
-        const float l_o = __shfl_xor_sync(0xffffffffu, st.l, o);
-        const float M = fmaxf(st.m, m_o);
-        const float s_a = (st.m == -INFINITY) ? 0.f : exp2f(st.m - M);
-        const float s_b = (m_o == -INFINITY) ? 0.f : exp2f(m_o - M);
-        st.l = st.l * s_a + l_o * s_b;
-        if (WANT_GRAD) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                st.acc[i].x = st.acc[i].x * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].x, o) * s_b;
-                st.acc[i].y = st.acc[i].y * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].y, o) * s_b;
-                st.acc[i].z = st.acc[i].z * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].z, o) * s_b;
-                st.acc[i].w = st.acc[i].w * s_a + __shfl_xor_sync(0xffffffffu, st.acc[i].w, o) * s_b;
-            }
-        }
-        st.m = M;
-    }
-    if (lane == 0) {
-        s_m[warp] = st.m;
-        s_l[warp] = st.l;
-        if (warp == 0) {
-            s_pos[0] = z0;
-            s_pos[1] = cos_pos;
-        }
-    }
-    if (WANT_GRAD && grp == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s_acc[warp][i * 8 + l8] = st.acc[i];
-    }
-    __syncthreads();
-    if (warp != 0) return;
-
-    // warp 0 merges the SC_WARPS warp states in warp order
-    float M = s_m[0];
-#pragma unroll
-    for (int w2 = 1; w2 < SC_WARPS; ++w2) M = fmaxf(M, s_m[w2]);
-    float sc[SC_WARPS], l = 0.f;
-#pragma unroll
-    for (int w2 = 0; w2 < SC_WARPS; ++w2) {
-        sc[w2] = (s_m[w2] == -INFINITY) ? 0.f : exp2f(s_m[w2] - M);
-        l += s_l[w2] * sc[w2];
-    }
-    // CE with target 0: logsumexp(z) - z_0 (loss.py:147), evaluated in base 2
-    if (lane == 0) {
-        loss_kq[k * Q + q] = 0.6931471805599453f * ((M + log2f(l)) - s_pos[0]);
-        anchor_px[k * Q + q] = pa;
-    }
-    if (WANT_GRAD) {
-        // dL/da = (sum_j g_j r_hat_j - (sum_j g_j cos_j) a_hat) / max(||a||, eps),  g_j = (pi_j - [j==0]) / (Q V temp)
-        // with sum_j pi_j r_hat_j = acc / l and sum_j pi_j cos_j = a_hat . (acc / l)        (SURVEY.md Appendix A.4)
-        const float inv_l = 1.f / l;
-        const float4* ap = rows + (size_t)pa * (CSS_D / 4);
-        const float4* php = proto_hat + (size_t)c * (CSS_D / 4);
-        float4 S[2], av[2], ph[2];
-        float sdot = 0.f;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int col = lane + 32 * h2;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int w2 = 0; w2 < SC_WARPS; ++w2) {
-                const float4 v = s_acc[w2][col];
-                t.x = fmaf(v.x, sc[w2], t.x);
-                t.y = fmaf(v.y, sc[w2], t.y);
-                t.z = fmaf(v.z, sc[w2], t.z);
-                t.w = fmaf(v.w, sc[w2], t.w);
-            }
-            S[h2] = make_float4(t.x * inv_l, t.y * inv_l, t.z * inv_l, t.w * inv_l);
-            av[h2] = __ldg(ap + col);                       // raw anchor -> a_hat
-            av[h2].x *= inv_na; av[h2].y *= inv_na; av[h2].z *= inv_na; av[h2].w *= inv_na;
-            ph[h2] = __ldg(php + col);
-            sdot += S[h2].x * av[h2].x + S[h2].y * av[h2].y + S[h2].z * av[h2].z + S[h2].w * av[h2].w;
-        }
-        sdot = warp_sum(sdot);
-        const float scale = 1.f / ((float)Q * (float)V * temp);
-        const float tt = (sdot - s_pos[1]) * scale;
-        float4* g = grad_anchor + ((size_t)k * Q + q) * (CSS_D / 4);
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            float4 o;
-            o.x = ((S[h2].x - ph[h2].x) * scale - tt * av[h2].x) * inv_na;
-            o.y = ((S[h2].y - ph[h2].y) * scale - tt * av[h2].y) * inv_na;
-            o.z = ((S[h2].z - ph[h2].z) * scale - tt * av[h2].z) * inv_na;
-            o.w = ((S[h2].w - ph[h2].w) * scale - tt * av[h2].w) * inv_na;
-            g[lane + 32 * h2] = o;
-        }
-    }
+    finish_query<WANT_GRAD>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
 }
 
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.

@@ -254,20 +254,30 @@ struct Taps {
     float hx, lx, hy, ly;
 };
 
-// softmax + max over the C up-sampled values of one map; `src` is the staged tile ([C][cstride]) or the global map
-template <bool USE_TEMP>
-__device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ src, int C, int cstride, const Taps& t, float temp,
-                                                     float& conf, int& label) {
-    float v[CSS_CMAX];
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softmax + max over the C up-sampled values of one map; `src` is the staged tile ([C][cstride]) or the global map.
+// CT > 0: compile-time class count (no predicated-off iterations); CT == 0: any C <= 32.
+// tmode: 0 = no temperature, 1 = x * rtemp is exactly x / temp (temp a power of two), 2 = IEEE division by temp.
+template <int CT>
+__device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ src, int C, int cstride, const Taps& t, int tmode,
+                                                     float temp, float rtemp, float& conf, int& label) {
+    constexpr int CN = CT > 0 ? CT : CSS_CMAX;
+    float v[CN];
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < CSS_CMAX; ++c) {
-        if (c < C) {
+    for (int c = 0; c < CN; ++c) {
+        if (CT > 0 || c < C) {
             const float* s = src + c * cstride;
             float top = __fadd_rn(__fmul_rn(t.hx, s[t.o00]), __fmul_rn(t.lx, s[t.o01]));
             float bot = __fadd_rn(__fmul_rn(t.hx, s[t.o10]), __fmul_rn(t.lx, s[t.o11]));
             float val = __fadd_rn(__fmul_rn(t.hy, top), __fmul_rn(t.ly, bot));
-            if (USE_TEMP) val = __fdiv_rn(val, temp);
+            if (tmode == 1) val = __fmul_rn(val, rtemp);
+            else if (tmode == 2) val = __fdiv_rn(val, temp);
             v[c] = val;
             m = fmaxf(m, val);
         }
@@ -275,9 +285,9 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
     float sum = 0.f;
     float emax = 0.f;
 #pragma unroll
-    for (int c = 0; c < CSS_CMAX; ++c) {
-        if (c < C) {
-            v[c] = __expf(v[c] - m);          // exp(0) == 1 exactly for the arg-max, monotone elsewhere
+    for (int c = 0; c < CN; ++c) {
+        if (CT > 0 || c < C) {
+            v[c] = ex2_approx((v[c] - m) * 1.4426950408889634f);   // exp(x - m): exactly 1 for the arg-max, monotone elsewhere
             sum += v[c];
             emax = fmaxf(emax, v[c]);
         }
@@ -285,15 +295,15 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
     // torch.max(softmax): the largest e_c/sum, first index on ties (ties after rounding included)
     int lab = 0;
 #pragma unroll
-    for (int c = CSS_CMAX - 1; c >= 0; --c)
-        if (c < C && v[c] == emax) lab = c;
+    for (int c = CN - 1; c >= 0; --c)
+        if ((CT > 0 || c < C) && v[c] == emax) lab = c;
     conf = __fdiv_rn(emax, sum);
     label = lab;
 }
 
-template <bool STAGED>
+template <bool STAGED, int CT>
 __global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
-    const float* __restrict__ sim, const float* __restrict__ logits, float temp, int fuse_mode, int C, int h, int w, int H, int W,
+    const float* __restrict__ sim, const float* __restrict__ logits, float temp, float rtemp, int tmode, int fuse_mode, int C, int h, int w, int H, int W,
     float ry, float rx, int tile_cap, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
     int64_t* __restrict__ label_cls, float* __restrict__ fused) {
     extern __shared__ float tile[];                 // [2 maps][C][in_th * in_tw]  (STAGED only)
@@ -339,15 +349,15 @@ __global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
     int lr = -1, lc = -2;
     if (sim) {
         float cf;
-        if (STAGED) upsample_softmax_max<true>(tile, C, cstride, t, temp, cf, lr);
-        else upsample_softmax_max<true>(sim + (size_t)b * C * hw, C, hw, t, temp, cf, lr);
+        if (STAGED) upsample_softmax_max<CT>(tile, C, cstride, t, tmode, temp, rtemp, cf, lr);
+        else upsample_softmax_max<CT>(sim + (size_t)b * C * hw, C, hw, t, tmode, temp, rtemp, cf, lr);
         if (conf_rep) conf_rep[o] = cf;
         if (label_rep) label_rep[o] = lr;
     }
     if (logits) {
         float cf;
-        if (STAGED) upsample_softmax_max<false>(tile + C * tile_cap, C, cstride, t, 1.f, cf, lc);
-        else upsample_softmax_max<false>(logits + (size_t)b * C * hw, C, hw, t, 1.f, cf, lc);
+        if (STAGED) upsample_softmax_max<CT>(tile + C * tile_cap, C, cstride, t, 0, 1.f, 1.f, cf, lc);
+        else upsample_softmax_max<CT>(logits + (size_t)b * C * hw, C, hw, t, 0, 1.f, 1.f, cf, lc);
         if (conf_cls) conf_cls[o] = cf;
         if (label_cls) label_cls[o] = lc;
     }
@@ -376,17 +386,27 @@ extern "C" int css_upsample_label_fuse(const float* sim, const float* logits, fl
     const size_t smem = (size_t)2 * C * tile_cap * sizeof(float);
     dim3 grid((W + K2_TW - 1) / K2_TW, (H + K2_TH - 1) / K2_TH, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // x / temp == x * (1/temp) exactly when temp is a power of two (the shipped 0.5 / 0.25); otherwise divide like the reference
+    int texp;
+    const int tmode = (frexpf(temp, &texp) == 0.5f) ? 1 : 2;
+    const float rtemp = 1.f / temp;
+#define K2_LAUNCH(STG, CTV, SM)                                                                                                     \
+    upsample_label_fuse_kernel<STG, CTV><<<grid, K2_TH * K2_TW, SM, st>>>(sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, \
+                                                                         rx, tile_cap, conf_rep, label_rep, conf_cls, label_cls, fused)
     if (smem <= 96 * 1024) {
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) { css_set_error("css_upsample_label_fuse: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         }
-        upsample_label_fuse_kernel<true><<<grid, K2_TH * K2_TW, smem, st>>>(sim, logits, temp, fuse_mode, C, h, w, H, W, ry, rx, tile_cap,
-                                                                            conf_rep, label_rep, conf_cls, label_cls, fused);
+        if (C == 21) K2_LAUNCH(true, 21, smem);          // VOC
+        else if (C == 19) K2_LAUNCH(true, 19, smem);     // CityScapes
+        else K2_LAUNCH(true, 0, smem);
     } else {   // strong down-sampling: the footprint does not fit, read the taps from global memory
-        upsample_label_fuse_kernel<false><<<grid, K2_TH * K2_TW, 0, st>>>(sim, logits, temp, fuse_mode, C, h, w, H, W, ry, rx, 0,
-                                                                          conf_rep, label_rep, conf_cls, label_cls, fused);
+        K2_LAUNCH(false, 0, 0);
     }
+#undef K2_LAUNCH
     CSS_CHECK_LAUNCH("css_upsample_label_fuse", 1);
     return 0;
 }
