@@ -141,6 +141,27 @@ __device__ __forceinline__ float group_sum8(float v) {     // reduce over the 8 
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// same dot with the anchor slice re-read from shared memory for every row (volatile asm: not hoisted), so that the 32
+// anchor registers per lane are free and a fifth CTA fits on the SM
+__device__ __forceinline__ float dot8_smem(uint32_t a_addr, const float4 (&r)[8]) {
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float4 a0 = lds128(a_addr + i * 128), a1 = lds128(a_addr + (i + 1) * 128);
+        s0 = __ffma2_rn(make_float2(a0.x, a0.y), make_float2(r[i].x, r[i].y), s0);
+        s1 = __ffma2_rn(make_float2(a0.z, a0.w), make_float2(r[i].z, r[i].w), s1);
+        s2 = __ffma2_rn(make_float2(a1.x, a1.y), make_float2(r[i + 1].x, r[i + 1].y), s2);
+        s3 = __ffma2_rn(make_float2(a1.z, a1.w), make_float2(r[i + 1].z, r[i + 1].w), s3);
+    }
+    return ((s0.x + s0.y) + (s1.x + s1.y)) + ((s2.x + s2.y) + (s3.x + s3.y));
+}
+
 // 32-element slice dot with packed fp32x2 FMAs, 4 independent chains
 __device__ __forceinline__ float dot8(const float4 (&a)[8], const float4 (&r)[8]) {
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
@@ -152,6 +173,12 @@ __device__ __forceinline__ float dot8(const float4 (&a)[8], const float4 (&r)[8]
         s3 = __ffma2_rn(hi2(a[i + 1]), hi2(r[i + 1]), s3);
     }
     return ((s0.x + s0.y) + (s1.x + s1.y)) + ((s2.x + s2.y) + (s3.x + s3.y));
+}
+
+template <bool ASMEM, int NA>
+__device__ __forceinline__ float score_dot(const float4 (&a)[NA], uint32_t a_addr, const float4 (&r)[8]) {
+    if constexpr (ASMEM) return dot8_smem(a_addr, r);
+    else return dot8(a, r);
 }
 
 struct Online {            // online softmax state (base 2) of one 8-lane group
@@ -300,8 +327,8 @@ __device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos
     }
 }
 
-template <bool WANT_GRAD, bool PREFETCH>
-__global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel(
+template <bool WANT_GRAD, bool PREFETCH, bool ASMEM>
+__global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) score_ce_kernel(
     const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
@@ -327,12 +354,17 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel
     const DrawKey dk = make_key(seed, offset);
     const int ai = anchor_idx ? anchor_idx[k * Q + q] : draw_anchor(dk, k, q, n_hard);
     const int pa = hard_list[(size_t)c * N + ai];
-    float4 a[8];
-    {
+    __shared__ float4 s_a[ASMEM ? CSS_D / 4 : 1];
+    float4 a[ASMEM ? 1 : 8];
+    if (ASMEM) {
+        if (threadIdx.x < CSS_D / 4) s_a[threadIdx.x] = __ldg(rows + (size_t)pa * (CSS_D / 4) + threadIdx.x);
+        __syncthreads();
+    } else {
         const float4* ap = rows + (size_t)pa * (CSS_D / 4) + l8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = __ldg(ap + i * 8);
+        for (int i = 0; i < (ASMEM ? 1 : 8); ++i) a[i] = __ldg(ap + i * 8);
     }
+    const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(&s_a[ASMEM ? l8 : 0]);
     const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);       // cosine_similarity eps (loss.py:146)
     const float4* pp = proto_hat + (size_t)c * (CSS_D / 4) + l8;
     const float scale2 = 1.4426950408889634f / temp;          // logits in base 2: z2 = cos * log2(e) / temp
@@ -392,7 +424,7 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel
 #pragma unroll
                     for (int i = 0; i < 8; ++i) rn[i] = __ldg(p + i * 8);
                 }
-                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                const float cosv = group_sum8(score_dot<ASMEM>(a, a_addr, r)) * (inv_na * inv);
                 const float z = cosv * scale2;
                 if (row == -1) {
                     z0 = z;
@@ -409,7 +441,7 @@ __global__ void __launch_bounds__(SC_THREADS, WANT_GRAD ? 4 : 5) score_ce_kernel
                 float4 r[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
-                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                const float cosv = group_sum8(score_dot<ASMEM>(a, a_addr, r)) * (inv_na * inv);
                 const float z = cosv * scale2;
                 if (row == -1) {
                     z0 = z;
@@ -455,11 +487,11 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(Q, C);
     if (grad_anchor)
-        score_ce_kernel<true, false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
+        score_ce_kernel<true, false, true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                           temp, loss_kq, anchor_px, (float4*)grad_anchor);
     else
-        score_ce_kernel<false, true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
+        score_ce_kernel<false, true, false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
                                                            valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                            temp, loss_kq, anchor_px, nullptr);
     loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);
@@ -470,13 +502,27 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
 // -------------------------------------------------------------------------------------------------------------------
 // backward: grad_rep = 0 ; grad_rep[b, :, y, x] += grad_out * grad_anchor[kq, :] at every anchor pixel
 // -------------------------------------------------------------------------------------------------------------------
+#define GS_PER_BLOCK 8
+// each CTA handles GS_PER_BLOCK anchors: all pixel ids and gradient rows are loaded first (independent loads), then the
+// red.global.add.f32 are issued; thread d owns channel d (stride h*w in the NCHW gradient)
 __global__ void __launch_bounds__(CSS_D) grad_scatter_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
-                                                             const float* __restrict__ grad_anchor, int hw, float* __restrict__ grad_rep) {
-    const int px = anchor_px[blockIdx.x];
-    if (px < 0) return;
-    const int b = px / hw, s = px - b * hw;
-    const float g = __ldg(grad_out) * grad_anchor[(size_t)blockIdx.x * CSS_D + threadIdx.x];
-    atomicAdd(grad_rep + ((size_t)b * CSS_D + threadIdx.x) * hw + s, g);
+                                                             const float* __restrict__ grad_anchor, int n_anchor, int hw,
+                                                             float* __restrict__ grad_rep) {
+    const int base = blockIdx.x * GS_PER_BLOCK;
+    int px[GS_PER_BLOCK];
+    float g[GS_PER_BLOCK];
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i) px[i] = (base + i < n_anchor) ? __ldg(anchor_px + base + i) : -1;
+    const float go = __ldg(grad_out);
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i)
+        g[i] = (px[i] >= 0) ? ldg_stream(grad_anchor + (size_t)(base + i) * CSS_D + threadIdx.x) : 0.f;
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i) {
+        if (px[i] < 0) continue;
+        const int b = px[i] / hw, s = px[i] - b * hw;
+        atomicAdd(grad_rep + ((size_t)b * CSS_D + threadIdx.x) * hw + s, go * g[i]);
+    }
 }
 
 extern "C" int css_grad_scatter(const float* grad_out, const int32_t* anchor_px, const float* grad_anchor, int n_anchor, int B2,
@@ -487,7 +533,8 @@ extern "C" int css_grad_scatter(const float* grad_out, const int32_t* anchor_px,
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(grad_rep, 0, sizeof(float) * (size_t)B2 * D * h * w, st);
     if (e != cudaSuccess) { css_set_error("css_grad_scatter: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    grad_scatter_kernel<<<n_anchor, CSS_D, 0, st>>>(grad_out, anchor_px, grad_anchor, h * w, grad_rep);
+    grad_scatter_kernel<<<(n_anchor + GS_PER_BLOCK - 1) / GS_PER_BLOCK, CSS_D, 0, st>>>(grad_out, anchor_px, grad_anchor, n_anchor, h * w,
+                                                                                      grad_rep);
     CSS_CHECK_LAUNCH("css_grad_scatter", 1);
     return 0;
 }
