@@ -405,9 +405,13 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "score_ce_kernel (css_score_ce)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "dram_gbs": (traffic / (score_avg_ms * 1e-3) / 1e9) if (traffic and score_avg_ms > 0) else None,
+                "l2_served_frac": (1.0 - traffic / gather_b) if (traffic and gather_b) else None,
                 "algorithmic_bytes_per_launch": gather_b, "avg_launch_ms": score_avg_ms, "share_of_step": score_avg_ms / ms_per_step,
-                "note": "logical 1 KB row gathers; the pixel-major copy is largely L2-resident at this size, so a fraction "
-                        "above 1.0 would be L2 service (SURVEY.md 8(d) honesty note)",
+                "note": "achieved counts LOGICAL 1 KB row gathers (SURVEY.md 8(d)); the 107 MB pixel-major copy is mostly L2 "
+                        "resident at this size, so frac > 1 is L2 service, not HBM: `traffic` (ncu dram bytes per launch) and "
+                        "`dram_gbs` say what really reached HBM; the kernel is bound by the L2->SM gather path (~17-19 TB/s "
+                        "measured ceiling for random 1 KB rows, tools/dev/dev_gather.cu)",
                 "path": {"bytes_stream": stream_b, "bytes_gather": gather_b,
                          "achieved_gbs": (stream_b + gather_b) / (ms_per_step * 1e-3) / 1e9,
                          "frac": (stream_b + gather_b) / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -431,7 +435,14 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL work must be released before the communicator goes away; then leave without the
+        # interpreter's atexit teardown, which can deadlock on a communicator that was used inside a captured graph
+        graph = e2e_graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -500,11 +500,14 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// backward: grad_rep = 0 ; grad_rep[b, :, y, x] += grad_out * grad_anchor[kq, :] at every anchor pixel
+// backward: grad_rep = 0 ; grad_rep[b, :, y, x] += grad_out * grad_anchor[kq, :] at every anchor pixel.
+// Autograd needs the dense [B2, 256, h, w] tensor, so the compulsory traffic is one streaming write of it: a linear
+// memset (the only pattern that writes this NCHW buffer at HBM speed: single-pass variants that fold the anchor rows into
+// a per-plane or flat sweep were measured 2x slower) followed by <= V*Q*256 red.global.add.f32.
 // -------------------------------------------------------------------------------------------------------------------
 #define GS_PER_BLOCK 8
 // each CTA handles GS_PER_BLOCK anchors: all pixel ids and gradient rows are loaded first (independent loads), then the
-// red.global.add.f32 are issued; thread d owns channel d (stride h*w in the NCHW gradient)
+// reductions are issued; thread d owns channel d (stride h*w in the NCHW gradient)
 __global__ void __launch_bounds__(CSS_D) grad_scatter_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
                                                              const float* __restrict__ grad_anchor, int n_anchor, int hw,
                                                              float* __restrict__ grad_rep) {

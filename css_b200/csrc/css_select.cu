@@ -14,9 +14,11 @@ extern "C" int css_select_tiles(int N) { return (N + CSS_SEL_TILE - 1) / CSS_SEL
 __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const float* __restrict__ label, const float* __restrict__ mask,
                                                                        const float* __restrict__ prob, float strong, int C, int hw,
                                                                        int N, int T, uint32_t* __restrict__ valid_bits,
-                                                                       uint32_t* __restrict__ hard_bits, int32_t* __restrict__ tile_counts) {
+                                                                       uint32_t* __restrict__ hard_bits, int32_t* __restrict__ tile_counts,
+                                                                       int32_t* __restrict__ meta) {
     __shared__ int cnt[2 * CSS_CMAX];
     if (threadIdx.x < 2 * CSS_CMAX) cnt[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta[CSS_META_TICKET] = 0;      // ticket of the scan kernel's last-CTA election
     __syncthreads();
     const int p = blockIdx.x * CSS_SEL_TILE + threadIdx.x;
     uint32_t vb = 0, hb = 0;
@@ -55,50 +57,81 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const flo
     }
 }
 
-// One block: warp-per-row exclusive scan over the T tiles (in place), class totals and the present-class table into meta.
-__global__ void __launch_bounds__(1024) select_scan_kernel(int32_t* __restrict__ tile_counts, int C, int T, int32_t* __restrict__ meta) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < 2 * C; r += 32) {
-        int32_t* row = tile_counts + (size_t)r * T;
-        const int len = (T + 31) / 32;
-        const int b0 = min(lane * len, T), b1 = min(b0 + len, T);
-        int tot = 0;
-        for (int i = b0; i < b1; ++i) tot += row[i];
-        int inc = tot;
+// One CTA per tile_counts row (2C rows): exclusive scan over the T tiles in place.  Thread t owns a contiguous segment
+// (independent loads), the 256 segment totals are scanned with shuffles.  The CTA that finishes last (ticket in
+// meta[CSS_META_TICKET], zeroed by the classify kernel) assembles class totals and the present-class table into meta.
+#define SCAN_THREADS 256
+#define SCAN_MAXSEG 16
+__global__ void __launch_bounds__(SCAN_THREADS) select_scan_kernel(int32_t* __restrict__ tile_counts, int C, int T, int32_t* __restrict__ meta) {
+    __shared__ int wsum[SCAN_THREADS / 32];
+    __shared__ int is_last;
+    const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int32_t* row = tile_counts + (size_t)r * T;
+    const int len = (T + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b0 = min(tid * len, T), b1 = min(b0 + len, T);
+    int vals[SCAN_MAXSEG];
+    int tot = 0;
+    if (len <= SCAN_MAXSEG) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
+        for (int i = 0; i < SCAN_MAXSEG; ++i) vals[i] = (b0 + i < b1) ? row[b0 + i] : 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_MAXSEG; ++i) tot += vals[i];
+    } else {
+        for (int i = b0; i < b1; ++i) tot += row[i];
+    }
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < SCAN_THREADS / 32; ++w2) {
+        if (w2 < warp) woff += wsum[w2];
+        total += wsum[w2];
+    }
+    int run = woff + inc - tot;
+    if (len <= SCAN_MAXSEG) {
+#pragma unroll
+        for (int i = 0; i < SCAN_MAXSEG; ++i) {
+            if (b0 + i < b1) row[b0 + i] = run;
+            run += vals[i];
         }
-        int run = inc - tot;
+    } else {
         for (int i = b0; i < b1; ++i) {
             const int v = row[i];
             row[i] = run;
             run += v;
         }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) {
-            const int kind = r / C, c = r - kind * C;
-            meta[(kind ? CSS_META_N_HARD : CSS_META_N_VALID) + c] = total;
-        }
+    }
+    if (tid == 0) {
+        const int kind = r / C, c = r - kind * C;
+        meta[(kind ? CSS_META_N_HARD : CSS_META_N_VALID) + c] = total;
+        __threadfence();
+        is_last = (atomicAdd(meta + CSS_META_TICKET, 1) == 2 * C - 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (is_last && tid == 0) {
+        __threadfence();
+        volatile int32_t* vm = meta;
         int V = 0;
         for (int c = 0; c < CSS_CMAX; ++c) {
             if (c >= C) {
-                meta[CSS_META_N_VALID + c] = 0;
-                meta[CSS_META_N_HARD + c] = 0;
+                vm[CSS_META_N_VALID + c] = 0;
+                vm[CSS_META_N_HARD + c] = 0;
             }
-            if (c < C && meta[CSS_META_N_VALID + c] > 0) {       // classes with no local valid pixel are skipped (loss.py:96-97)
-                meta[CSS_META_CLS_OF_SLOT + V] = c;
-                meta[CSS_META_SLOT_OF_CLS + c] = V++;
+            if (c < C && vm[CSS_META_N_VALID + c] > 0) {         // classes with no local valid pixel are skipped (loss.py:96-97)
+                vm[CSS_META_CLS_OF_SLOT + V] = c;
+                vm[CSS_META_SLOT_OF_CLS + c] = V++;
             } else {
-                meta[CSS_META_SLOT_OF_CLS + c] = -1;
+                vm[CSS_META_SLOT_OF_CLS + c] = -1;
             }
         }
-        for (int k = V; k < CSS_CMAX; ++k) meta[CSS_META_CLS_OF_SLOT + k] = -1;
-        meta[CSS_META_V] = V;
+        for (int k = V; k < CSS_CMAX; ++k) vm[CSS_META_CLS_OF_SLOT + k] = -1;
+        vm[CSS_META_V] = V;
     }
 }
 
@@ -153,8 +186,8 @@ extern "C" int css_select(const float* label, const float* mask, const float* pr
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w, N = B2 * hw, T = css_select_tiles(N);
     select_classify_kernel<<<T, CSS_SEL_TILE, 0, st>>>(label, mask, prob, strong_threshold, C, hw, N, T, valid_bits, hard_bits,
-                                                      tile_counts);
-    select_scan_kernel<<<1, 1024, 0, st>>>(tile_counts, C, T, meta);
+                                                      tile_counts, meta);
+    select_scan_kernel<<<2 * C, SCAN_THREADS, 0, st>>>(tile_counts, C, T, meta);
     select_scatter_kernel<<<T, CSS_SEL_TILE, 0, st>>>(valid_bits, hard_bits, tile_counts, C, N, T, valid_list, hard_list);
     CSS_CHECK_LAUNCH("css_select", 3);
     return 0;

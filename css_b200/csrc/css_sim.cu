@@ -97,12 +97,29 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) v[u][j] = ldg_stream(x[j] + (size_t)(d0 + u) * hw);
             if (ROWS) {
+                // Transposed write-out straight from registers.  A lane holds 64 contiguous bytes (16 channels) of its pixel's
+                // row; neighbouring lanes (pixels p, p+1) first swap 16-byte chunks so that every 128-bit store instruction
+                // completes whole 32-byte sectors (lane pair -> one sector) instead of half sectors.
+                const int odd = psub & 1;
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) {
-                    if (pix[j] < N) {
-                        float4* r = reinterpret_cast<float4*>(rows + (size_t)pix[j] * CSS_D + ks * DS + d0);
+                    const int pA = pix[j] - odd, pB = pA + 1;
+                    float* rA = rows + (size_t)pA * CSS_D + ks * DS + d0 + 4 * odd;
+                    float* rB = rA + CSS_D;
 #pragma unroll
-                        for (int u = 0; u < SM_U; u += 4) r[u / 4] = make_float4(v[u][j], v[u + 1][j], v[u + 2][j], v[u + 3][j]);
+                    for (int hh = 0; hh < SM_U / 8; ++hh) {
+                        const int ue = 8 * hh, uo = 8 * hh + 4;          // even / odd 16-byte chunk of this 32-byte sector
+                        float4 own_e = make_float4(v[ue][j], v[ue + 1][j], v[ue + 2][j], v[ue + 3][j]);
+                        float4 own_o = make_float4(v[uo][j], v[uo + 1][j], v[uo + 2][j], v[uo + 3][j]);
+                        float4 snd = odd ? own_e : own_o, rcv;
+                        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1);
+                        rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1);
+                        rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                        const float4 first = odd ? rcv : own_e;          // pixel pA: even lane -> chunk e, odd lane -> chunk o
+                        const float4 second = odd ? own_o : rcv;         // pixel pB
+                        if (pA < N) *reinterpret_cast<float4*>(rA + 8 * hh) = first;
+                        if (pB < N) *reinterpret_cast<float4*>(rB + 8 * hh) = second;
                     }
                 }
             }

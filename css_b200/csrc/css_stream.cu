@@ -72,18 +72,19 @@ __global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const float4* __
     if (t == 0) touched[blockIdx.x] = seen;
 }
 
-// deterministic second stage: block c first compacts the ids of the CTAs that touched class c (ballot order = CTA order);
-// the list is cut into CR_SEG contiguous segments, thread (seg, d) adds its segment's partials 8 loads at a time, and
-// the segment sums are combined in segment order: always the same association, whatever the timing.
-#define CR_SEG 4
-__global__ void __launch_bounds__(CSS_D * CR_SEG) class_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
-                                                                      const int32_t* __restrict__ meta, int G, int C,
-                                                                      float* __restrict__ class_stats) {
+// deterministic second stage: block (c, chunk) first compacts the ids of the CTAs that touched class c (ballot order =
+// CTA order); the list is cut into CR_SEG contiguous segments, thread (seg, d) adds its segment's partials 8 loads at a
+// time, and the segment sums are combined in segment order: always the same association, whatever the timing.
+#define CR_SEG 16
+#define CR_DCH 64                      // channels per block
+__global__ void __launch_bounds__(CR_DCH * CR_SEG) class_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
+                                                                       const int32_t* __restrict__ meta, int G, int C,
+                                                                       float* __restrict__ class_stats) {
     extern __shared__ int glist[];                 // [G]
-    __shared__ int wtot[CSS_D * CR_SEG / 32];
-    __shared__ float segsum[CR_SEG][CSS_D];
+    __shared__ int wtot[CR_DCH * CR_SEG / 32];
+    __shared__ float segsum[CR_SEG][CR_DCH];
     __shared__ int n_list;
-    constexpr int NT = CSS_D * CR_SEG, NW = NT / 32;
+    constexpr int NT = CR_DCH * CR_SEG, NW = NT / 32;
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) n_list = 0;
     __syncthreads();
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(CSS_D * CR_SEG) class_reduce_kernel(const floa
         __syncthreads();
     }
     const int n = n_list;
-    const int seg = tid / CSS_D, d = tid - seg * CSS_D;
+    const int seg = tid / CR_DCH, dl = tid - seg * CR_DCH, d = blockIdx.y * CR_DCH + dl;
     const int per = (n + CR_SEG - 1) / CR_SEG;
     const int i0 = min(seg * per, n), i1 = min(i0 + per, n);
     float acc = 0.f;
@@ -118,12 +119,12 @@ __global__ void __launch_bounds__(CSS_D * CR_SEG) class_reduce_kernel(const floa
         for (int u = 0; u < 8; ++u) acc += v[u];
     }
     for (; i < i1; ++i) acc += partials[((size_t)glist[i] * C + c) * CSS_D + d];
-    segsum[seg][d] = acc;
+    segsum[seg][dl] = acc;
     __syncthreads();
     if (seg == 0) {
-        float tot = segsum[0][d];
+        float tot = segsum[0][dl];
 #pragma unroll
-        for (int s2 = 1; s2 < CR_SEG; ++s2) tot += segsum[s2][d];
+        for (int s2 = 1; s2 < CR_SEG; ++s2) tot += segsum[s2][dl];
         class_stats[c * (CSS_D + 1) + d] = tot;
         if (d == 0) class_stats[c * (CSS_D + 1) + CSS_D] = (float)meta[CSS_META_N_VALID + c];
     }
@@ -137,7 +138,7 @@ extern "C" int css_class_stats(const float* rows, const uint32_t* valid_bits, co
     cudaStream_t st = (cudaStream_t)stream;
     const int G = css_class_blocks(N);
     class_sums_kernel<<<G, CS_THREADS, 0, st>>>((const float4*)rows, valid_bits, C, N, (float4*)partials, touched);
-    class_reduce_kernel<<<C, CSS_D * CR_SEG, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
+    class_reduce_kernel<<<dim3(C, CSS_D / CR_DCH), CR_DCH * CR_SEG, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
     CSS_CHECK_LAUNCH("css_class_stats", 2);
     return 0;
 }

@@ -54,6 +54,7 @@ extern "C" {
 #define CSS_META_N_HARD       64     /* [32] hard-pixel count per class                           */
 #define CSS_META_CLS_OF_SLOT  96     /* [32] class id of the k-th present class (increasing)      */
 #define CSS_META_SLOT_OF_CLS  128    /* [32] slot of a class, -1 when absent                      */
+#define CSS_META_TICKET       160    /* internal: last-CTA election of the scan kernel            */
 
 int         css_version(void);
 const char* css_last_error(void);
