@@ -97,6 +97,12 @@ def main():
     def scatter(i):
         check(lib.css_grad_scatter(ptr(one), ptr(anchor_px), ptr(grad_anchor), C * Q, B2, D, h, w, ptr(grads[i % P]), stream_ptr()), "scatter")
 
+    g0 = torch.Generator().manual_seed(0)
+    ll = torch.randint(-1, C, (B, H, W), generator=g0).to(dev)
+    lu = torch.randint(-1, C, (B, H, W), generator=g0).to(dev)
+    cu = torch.rand(B, H, W, generator=g0).to(dev)
+    res["threshold_glue K0 (8(f)-1, not in path sum)"] = timeit(
+        lambda i: css_b200.ops.threshold_glue(ll, lu, cu, 0.7, C, (h, w), "mix" if cfg["strategy"] == "mix" else "ori"), a.iters)
     res["select (3 kernels)"] = timeit(select, a.iters)
     res["class_stats (+reduce)"] = timeit(stream, a.iters)
     res["rep_rows only (ori flow)"] = timeit(lambda i: css_b200.ops.rep_rows(rep_all[i % P]), a.iters)
@@ -104,9 +110,9 @@ def main():
     res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
     res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
     res["grad_scatter (+memset)"] = timeit(scatter, a.iters)
-    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)"))
+    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)", "threshold_glue K0 (8(f)-1, not in path sum)"))
     for k, v in res.items():
-        print(f"{k:34s} {v:9.1f} us")
+        print(f"{k:46s} {v:9.1f} us")
     print(f"{'sum (path)':34s} {tot:9.1f} us")
     print(json.dumps({"workload": a.workload, "us": res}))
 
