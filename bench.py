@@ -352,33 +352,55 @@ def main():
     # ---- e2e: host buffers, H2D of every input + D2H of the loss inside the timed region -----------------------------------
     keys = ["rep_u", "pred_u", "rep_all", "label", "mask"] if strategy != "ori" else ["pred_u", "rep_all", "label", "mask", "prob_ori"]
     pinned = {k: host[k].pin_memory() for k in keys}
-    staged = {k: torch.empty_like(gpu[k]) for k in keys}
+    # two staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i; every step still uploads all
+    # of its inputs from pinned host memory and reads its loss back
+    staged = [{k: torch.empty_like(gpu[k]) for k in keys} for _ in range(2)]
+    for st_set in staged:
+        for k in gpu:
+            if k not in keys:
+                st_set[k] = gpu[k]
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]      # inputs of the set have landed
+    done = [torch.cuda.Event(), torch.cuda.Event()]       # the step that read the set has finished
 
-    e2e_graph = None
+    e2e_graphs = [None, None]
     if use_graph:
         try:
-            e2e_graph, e2e_out = capture(staged)
+            e2e_graphs = [capture(staged[0]), capture(staged[1])]
         except Exception as e:
             sys.stderr.write(f"bench: e2e graph capture failed ({e!r}); eager\n")
+            e2e_graphs = [None, None]
 
-    def e2e_step():
-        for k in keys:
-            staged[k].copy_(pinned[k], non_blocking=True)
-        if e2e_graph is not None:
-            e2e_graph.replay()
-            loss = e2e_out[0]
-        else:
-            loss, grad = step(staged)
-        return float(loss.item())             # D2H read of the step's result (synchronises)
+    def upload(i):
+        s_ = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[s_])
+            for k in keys:
+                staged[s_][k].copy_(pinned[k], non_blocking=True)
+            ready[s_].record(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        for ev in done:
+            ev.record()
+        upload(0)
+        for i in range(n):
+            s_ = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s_])
+            if e2e_graphs[s_] is not None:
+                e2e_graphs[s_][0].replay()
+                loss = e2e_graphs[s_][1][0]
+            else:
+                loss, grad = step(staged[s_])
+            done[s_].record()
+            float(loss.item())                # D2H read of the step's result (synchronises)
+
+    e2e_run(4)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.e2e_steps):
-        e2e_step()
+    e2e_run(args.e2e_steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -437,7 +459,8 @@ def main():
     if world > 1:
         # graphs that captured NCCL work must be released before the communicator goes away; then leave without the
         # interpreter's atexit teardown, which can deadlock on a communicator that was used inside a captured graph
-        graph = e2e_graph = None
+        graph = None
+        e2e_graphs = [None, None]
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()

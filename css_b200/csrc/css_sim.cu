@@ -43,14 +43,22 @@ __global__ void __launch_bounds__(CSS_D) proto_prep_kernel(const float* __restri
 //   * the two channel slices are combined with one xor-shuffle per value (fixed order: deterministic).
 // A warp reads 2 x 64 contiguous bytes per (channel pair, pixel group); the 4 warps of a CTA cover adjacent pixels.
 // ---------------------------------------------------------------------------------------------------------------
+// rep element loaders: fp32, or bf16 widened exactly to fp32 (all arithmetic stays fp32)
+__device__ __forceinline__ float ld_elem(const float* p) { return ldg_stream(p); }
+__device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) {
+    unsigned short u;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+    return __uint_as_float((uint32_t)u << 16);
+}
+
 #define SM_PPT 2
 #define SM_KS 2
 #define SM_U 16
 #define SM_WARPS 4
 #define SM_MINB 4
 
-template <int NG, bool ROWS>
-__global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const float* __restrict__ rep, const float* __restrict__ scratch,
+template <int NG, bool ROWS, typename T>
+__global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const T* __restrict__ rep, const float* __restrict__ scratch,
                                                                          int hw, int N, int C, int mode, float temp,
                                                                          float* __restrict__ out, float* __restrict__ rows,
                                                                          float* __restrict__ norms) {
@@ -72,7 +80,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
     const float4* myp = sp + (NG > 0 ? ks * SL : 0);
     const int n_wchunks = (N + WP - 1) / WP;
     for (int wc = blockIdx.x * SM_WARPS + warp; wc < n_wchunks; wc += gridDim.x * SM_WARPS) {
-        const float* x[SM_PPT];
+        const T* x[SM_PPT];
         int pix[SM_PPT];
 #pragma unroll
         for (int j = 0; j < SM_PPT; ++j) {
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
 #pragma unroll
             for (int u = 0; u < SM_U; ++u)
 #pragma unroll
-                for (int j = 0; j < SM_PPT; ++j) v[u][j] = ldg_stream(x[j] + (size_t)(d0 + u) * hw);
+                for (int j = 0; j < SM_PPT; ++j) v[u][j] = ld_elem(x[j] + (size_t)(d0 + u) * hw);
             if (ROWS) {
                 // Transposed write-out straight from registers.  A lane holds 64 contiguous bytes (16 channels) of its pixel's
                 // row; neighbouring lanes (pixels p, p+1) first swap 16-byte chunks so that every 128-bit store instruction
@@ -195,28 +203,28 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
     }
 }
 
-template <int NG, bool ROWS>
-static void launch_rep_pass(const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
+template <int NG, bool ROWS, typename T>
+static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
                             float* rows, float* norms, cudaStream_t st) {
     constexpr int WP = (32 / SM_KS) * SM_PPT;
     const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
     const int cap = css_cached_sm_count() * SM_MINB;
-    rep_pass_kernel<NG, ROWS><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out, rows,
+    rep_pass_kernel<NG, ROWS, T><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out, rows,
                                                                                         norms);
 }
 
-template <bool ROWS>
-static void dispatch_rep_pass(int ng, const float* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
+template <bool ROWS, typename T>
+static void dispatch_rep_pass(int ng, const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
                               float* rows, float* norms, cudaStream_t st) {
     switch (ng) {
-        case 1: launch_rep_pass<1, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 2: launch_rep_pass<2, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 3: launch_rep_pass<3, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 4: launch_rep_pass<4, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 5: launch_rep_pass<5, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 6: launch_rep_pass<6, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 7: launch_rep_pass<7, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        default: launch_rep_pass<8, ROWS>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 1: launch_rep_pass<1, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 2: launch_rep_pass<2, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 3: launch_rep_pass<3, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 4: launch_rep_pass<4, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 5: launch_rep_pass<5, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 6: launch_rep_pass<6, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 7: launch_rep_pass<7, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        default: launch_rep_pass<8, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
     }
 }
 
@@ -229,20 +237,26 @@ extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototy
     CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_rep_pass: non-positive size");
     CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX, CSS_E_ARG, "css_rep_pass: bad mode %d", mode);
     if (int e = css_check_dims(want_sim ? C : 1, D)) return e;
-    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32, CSS_E_DTYPE, "css_rep_pass: rep dtype %d not supported", rep_dtype);
+    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32 || rep_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_rep_pass: rep dtype %d not supported",
+                  rep_dtype);
     CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_rep_pass: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w, N = B * hw;
-    const float* r = (const float*)rep;
     int launches = 1;
     if (want_sim) {
         proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
         ++launches;
-        if (want_rows) dispatch_rep_pass<true>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);
-        else dispatch_rep_pass<false>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);
-    } else {
-        launch_rep_pass<0, true>(r, nullptr, hw, N, C, mode, temp, nullptr, rows, norms, st);
     }
+#define REP_PASS_RUN(TYPE)                                                                                                  \
+    do {                                                                                                                    \
+        const TYPE* r = (const TYPE*)rep;                                                                                   \
+        if (want_sim && want_rows) dispatch_rep_pass<true, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st); \
+        else if (want_sim) dispatch_rep_pass<false, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);      \
+        else launch_rep_pass<0, true, TYPE>(r, nullptr, hw, N, C, mode, temp, nullptr, rows, norms, st);                      \
+    } while (0)
+    if (rep_dtype == CSS_DTYPE_F32) REP_PASS_RUN(float);
+    else REP_PASS_RUN(__nv_bfloat16);
+#undef REP_PASS_RUN
     CSS_CHECK_LAUNCH("css_rep_pass", launches);
     return 0;
 }

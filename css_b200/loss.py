@@ -95,6 +95,7 @@ class _ContrastFn(torch.autograd.Function):
             e1.record()
             ev.append((e0, e1))
         ctx.shape = (B2, D, h, w)
+        ctx.rep_dtype = rep.dtype
         ctx.n_anchor = C * Q
         ctx.save_for_backward(anchor_px, grad_anchor)
         mod.last = dict(ws=ws, anchor_px=anchor_px, grad_anchor=grad_anchor, seed=seed, offset=offset, rows=rows, norms=norms,
@@ -113,6 +114,8 @@ class _ContrastFn(torch.autograd.Function):
         with torch.cuda.device(anchor_px.device):
             check(lib.css_grad_scatter(ptr(go), ptr(anchor_px), ptr(grad_anchor), ctx.n_anchor, B2, D, h, w, ptr(grad_rep),
                                        stream_ptr()), "css_grad_scatter")
+        if ctx.rep_dtype != torch.float32:
+            grad_rep = grad_rep.to(ctx.rep_dtype)
         return grad_rep, None, None, None, None, None, None, None, None
 
 
@@ -160,8 +163,8 @@ class Contrast_Loss(nn.Module):
         _indices: optional (anchor_idx int32 [C,Q], neg_idx int32 [C,Q,Nn]) slot-major device tensors of recorded draws."""
         if not rep.is_cuda:
             raise RuntimeError("css_b200: Contrast_Loss needs CUDA tensors (no CPU fallback)")
-        if rep.dtype != torch.float32:
-            raise RuntimeError(f"css_b200: rep must be float32, got {rep.dtype}")
+        if rep.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"css_b200: rep must be float32 or bfloat16, got {rep.dtype}")
         if not (prototypes.is_cuda and prototypes.dtype == torch.float32 and prototypes.is_contiguous()):
             raise RuntimeError("css_b200: prototypes must be a contiguous float32 CUDA tensor (it is updated in place)")
         if rep.shape[1] != _lib.D or prototypes.shape != (label.shape[1], _lib.D):

@@ -18,6 +18,17 @@ def _cuda_f32(t, name):
     return t.detach().contiguous()
 
 
+def _cuda_rep(t, name="rep"):
+    """Representation maps may be float32 or bfloat16 (BASELINE north_star); everything downstream is fp32."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"css_b200: `{name}` must be a CUDA tensor (no CPU fallback)")
+    if t.dtype == torch.float32:
+        return t.detach().contiguous(), _lib.DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return t.detach().contiguous(), _lib.DTYPE_BF16
+    raise RuntimeError(f"css_b200: `{name}` must be float32 or bfloat16, got {t.dtype}")
+
+
 def _proto_scratch(device):
     return torch.empty(_lib.D * _lib.CMAX, device=device, dtype=torch.float32)
 
@@ -52,19 +63,19 @@ def rows_key(rep):
 
 def rep_rows(rep):
     """Pixel-major copy rows [N,256] + norms [N] of an NCHW representation map (one streaming read)."""
-    rep = _cuda_f32(rep, "rep")
+    rep, dt = _cuda_rep(rep)
     B, D, h, w = rep.shape
     rows = torch.empty((B * h * w, D), device=rep.device, dtype=torch.float32)
     norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
-        check(lib.css_rep_pass(ptr(rep), _lib.DTYPE_F32, None, None, B, 1, D, h, w, _lib.SIM_COS, 1.0, None, ptr(rows), ptr(norms),
+        check(lib.css_rep_pass(ptr(rep), dt, None, None, B, 1, D, h, w, _lib.SIM_COS, 1.0, None, ptr(rows), ptr(norms),
                                stream_ptr()), "css_rep_pass")
     return rows, norms
 
 
 def _sim(rep, prototypes, mode, temp, with_rows=False):
-    rep = _cuda_f32(rep, "rep")
+    rep, dt = _cuda_rep(rep)
     prototypes = _cuda_f32(prototypes, "prototypes")
     B, D, h, w = rep.shape
     C = prototypes.shape[0]
@@ -78,7 +89,7 @@ def _sim(rep, prototypes, mode, temp, with_rows=False):
         norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
-        check(lib.css_rep_pass(ptr(rep), _lib.DTYPE_F32, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
+        check(lib.css_rep_pass(ptr(rep), dt, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
                                ptr(rows), ptr(norms), stream_ptr()), "css_rep_pass")
     if with_rows:
         out._css_rows = RowsCache(rep, rows, norms)

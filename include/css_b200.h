@@ -72,6 +72,7 @@ unsigned long long css_launch_count(void);
  *  (b) rows f32[N*D] + norms f32[N]: the pixel-major copy (row p = pixel id p, raw values) and ||x_p||, from which the
  *      loss gathers candidate rows and accumulates class sums (loss.py:85,102,111-112,142).
  * NULL sim_out skips (a); NULL rows/norms skips (b).  css_sim_map is (a) alone.
+ * rep_dtype: CSS_DTYPE_F32 or CSS_DTYPE_BF16 (bf16 is widened exactly; all arithmetic and all outputs stay fp32).
  */
 int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                  int B, int C, int D, int h, int w, int mode, float temp,

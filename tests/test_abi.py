@@ -50,7 +50,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     one = ctypes.c_void_p(16)
     assert lib.css_sim_map(one, 0, one, one, 1, 21, 128, 4, 4, 0, 0.5, one, None) == -2      # D != 256
     assert lib.css_sim_map(one, 0, one, one, 1, 33, 256, 4, 4, 0, 0.5, one, None) == -2      # C > 32
-    assert lib.css_sim_map(one, 1, one, one, 1, 21, 256, 4, 4, 0, 0.5, one, None) == -3      # bf16 not supported yet
+    assert lib.css_sim_map(one, 7, one, one, 1, 21, 256, 4, 4, 0, 0.5, one, None) == -3      # unknown rep dtype
 
 
 def test_ops_refuse_cpu_tensors():

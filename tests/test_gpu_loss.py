@@ -304,3 +304,29 @@ def test_model_shells_with_stub_network():
     finally:
         for k, v in saved.items():
             setattr(models.hooks, k, v)
+
+
+def test_bf16_rep_matches_fp32_path_on_widened_values():
+    """bf16 representation maps (north_star extension, tolerance rel 1e-2): the kernels widen bf16 exactly and compute in
+    fp32, so the result must equal the fp32 path on rep.float() -- far inside the stated 1e-2."""
+    import css_b200
+    from css_b200 import synth
+    B2, C, h, w, Q, Nn = 2, 21, 33, 31, 32, 64
+    d = synth.student_batch(B2, C, h, w, seed=9, strategy="mix", block=4)
+    rep16 = d["rep"].to(torch.bfloat16).cuda()
+    protos0 = synth.warm_prototypes(C, seed=4)
+    prob16 = css_b200.ops.proto_softmax_sim(rep16, protos0.cuda(), 0.5)
+    prob32 = css_b200.ops.proto_softmax_sim(rep16.float(), protos0.cuda(), 0.5)
+    assert torch.equal(prob16, prob32)
+    np.testing.assert_allclose(prob16.cpu().numpy(), O.proto_softmax_sim(rep16.float().cpu().numpy(), protos0.numpy(), 0.5), atol=1e-6)
+    outs = []
+    for rep in (rep16, rep16.float()):
+        crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.8, seed=3).cuda()
+        protos = protos0.clone().cuda()
+        r = rep.clone().requires_grad_(True)
+        loss = crit(r, d["label"].cuda(), d["mask"].cuda(), prob16, protos)
+        loss.backward()
+        assert r.grad.dtype == rep.dtype
+        outs.append((loss.item(), r.grad.float(), protos))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][2], outs[1][2])
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-2, atol=1e-6)
