@@ -34,7 +34,7 @@ SIGNATURES = {
     "css_class_stats": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, P, P, P]),
     "css_sample": (c_int, [P, P, c_uint64, c_uint64, c_int, c_int, c_int, P, P, P]),
-    "css_score_ce": (c_int, [P, P, P, P, P, P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_int, c_int, c_int, c_float,
+    "css_score_ce": (c_int, [P, P, P, P, P, P, P, P, P, c_uint64, c_uint64, P, c_int, c_int, c_int, c_int, c_int, c_float,
                              P, P, P, P, P]),
     "css_grad_scatter": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "css_threshold_glue": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),

@@ -84,12 +84,13 @@ class _ContrastFn(torch.autograd.Function):
         loss = torch.empty((), device=dev, dtype=torch.float32)
         a_idx, n_idx = (None, None) if indices is None else indices
         seed, offset = mod._next_draw_key()
+        counter = mod._device_counter(dev)
         ev = mod.score_events
         if ev is not None:                       # bench.py times the dominant kernel live, on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
-                               ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, N, C, D, Q, Nn,
+                               ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, ptr(counter), N, C, D, Q, Nn,
                                float(mod.temp), ptr(ws.loss_kq), ptr(anchor_px), ptr(grad_anchor), ptr(loss), st), "css_score_ce")
         if ev is not None:
             e1.record()
@@ -135,6 +136,7 @@ class Contrast_Loss(nn.Module):
         self.sync_prototypes = sync_prototypes   # extension, default off: the reference lets per-rank prototypes drift
         self._seed = seed
         self._step = 0
+        self._counter = None
         self._ws = None
         self.last = None
         self.score_events = None              # set to a list to collect (start, end) CUDA events around css_score_ce
@@ -142,15 +144,25 @@ class Contrast_Loss(nn.Module):
     # ---- sampler state: (seed, offset) of the device Philox stream; one offset per forward call -------------------
     def set_sampler(self, seed, step=0):
         self._seed, self._step = int(seed), int(step)
+        self._counter = None
+
+    def _device_counter(self, device):
+        """Device-resident step counter of the Philox stream: the kernels read it as the draw offset and bump it, so the
+        sampler advances without any host involvement (eager calls and CUDA-graph replays alike)."""
+        if self._counter is None or self._counter.device != device:
+            self._counter = torch.full((1,), self._step, device=device, dtype=torch.int64)
+        return self._counter
+
+    def draw_offset(self):
+        """Offset the NEXT forward will draw from (reads the device counter: synchronises; verification only)."""
+        return self._step if self._counter is None else int(self._counter.item())
 
     def _next_draw_key(self):
         if self._seed is None:   # derived from torch's CPU generator so torch.manual_seed() makes runs reproducible
             self._seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             if dist.is_available() and dist.is_initialized():
                 self._seed ^= 0x9E3779B97F4A7C15 * (dist.get_rank() + 1) & (2 ** 63 - 1)
-        off = self._step
-        self._step += 1
-        return self._seed & (2 ** 64 - 1), off
+        return self._seed & (2 ** 64 - 1), 0
 
     def _workspace(self, B2, C, D, h, w, device):
         key = (B2, C, D, h, w, self.num_queries, self.num_negatives, str(device))

@@ -143,13 +143,15 @@ int css_sample(const int32_t* meta, const float* class_cdf, uint64_t seed, uint6
 /* ---- stage 3: scoring + cross-entropy + d loss / d anchor ------------------------------------------------------------
  * Replaces loss.py:124-149 and its autograd backward up to the anchor rows.  rows / norms come from css_rep_pass.
  *   anchor_idx / neg_idx: as produced by css_sample or recorded from the reference; NULL = draw on the fly with
- *   (seed, offset), bit-identical to css_sample with the same arguments.
+ *   (seed, offset + *step_counter), bit-identical to css_sample with the same (seed, offset).
+ *   step_counter: optional DEVICE u64, read as an offset increment and incremented by one at the end of the call, so that
+ *   replays of a captured CUDA graph keep drawing fresh samples; NULL = use `offset` alone.
  *   loss_kq f32[C*Q], anchor_px i32[C*Q] (pixel id of each anchor, -1 if none), grad_anchor f32[C*Q*D] or NULL,
  *   loss f32[1] = (1/V) sum_k (1/Q) sum_q loss_kq, exactly 0 when V <= 1.
  */
 int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
                  const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta,
-                 const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset,
+                 const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset, uint64_t* step_counter,
                  int N, int C, int D, int Q, int Nn, float temp,
                  float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream);
 

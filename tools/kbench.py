@@ -88,7 +88,7 @@ def main():
 
     def score(i, grad=True):
         check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
-                               ptr(ws.hard_list), ptr(ws.meta), None, None, 7, i, N, C, D, Q, Nn, temp, ptr(ws.loss_kq),
+                               ptr(ws.hard_list), ptr(ws.meta), None, None, 7, i, None, N, C, D, Q, Nn, temp, ptr(ws.loss_kq),
                                ptr(anchor_px), ptr(grad_anchor) if grad else None, ptr(loss), stream_ptr()), "score")
 
     grads = [torch.empty(B2, D, h, w, device=dev) for _ in range(P)]
