@@ -327,13 +327,25 @@ __device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos
     }
 }
 
+// publishes the Philox offset of this call, offset + *step_counter, into meta and bumps the device-resident counter so the
+// next call -- or the next replay of a captured CUDA graph -- draws fresh samples
+__global__ void draw_offset_kernel(uint64_t offset, unsigned long long* __restrict__ step_counter, int32_t* __restrict__ meta) {
+    unsigned long long o = offset;
+    if (step_counter) {
+        o += *step_counter;
+        *step_counter += 1ull;
+    }
+    meta[CSS_META_DRAW_OFFSET] = (int32_t)(uint32_t)o;
+    meta[CSS_META_DRAW_OFFSET + 1] = (int32_t)(uint32_t)(o >> 32);
+}
+
 template <bool WANT_GRAD, bool PREFETCH, bool ASMEM>
 __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) score_ce_kernel(
     const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
-    uint64_t offset, const unsigned long long* __restrict__ step_counter, int N, int Q, int Nn, float temp,
-    float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px, float4* __restrict__ grad_anchor) {
+    uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
+    float4* __restrict__ grad_anchor) {
     __shared__ SlotTables tb;
     __shared__ QueryShared sh;
     const int k = blockIdx.y, q = blockIdx.x;
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     build_slot_tables(tb, meta, class_cdf, k, V);
 
     const int grp = lane >> 3, l8 = lane & 7;
-    const DrawKey dk = make_key(seed, offset + (step_counter ? *step_counter : 0ull));
+    const DrawKey dk = make_key(seed, ((uint64_t)(uint32_t)meta[CSS_META_DRAW_OFFSET + 1] << 32) | (uint32_t)meta[CSS_META_DRAW_OFFSET]);
     const int ai = anchor_idx ? anchor_idx[k * Q + q] : draw_anchor(dk, k, q, n_hard);
     const int pa = hard_list[(size_t)c * N + ai];
     __shared__ float4 s_a[ASMEM ? CSS_D / 4 : 1];
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
 
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_kq, const int32_t* __restrict__ meta, int Q,
-                                                          float* __restrict__ loss, unsigned long long* __restrict__ step_counter) {
+                                                          float* __restrict__ loss) {
     __shared__ float part[8];
     const int V = meta[CSS_META_V];
     float s = 0.f;
@@ -470,12 +482,11 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
         float t = 0.f;
         for (int i = 0; i < 8; ++i) t += part[i];
         *loss = (V > 1) ? t / ((float)Q * (float)V) : 0.f;
-        if (step_counter) *step_counter += 1ull;        // the next call (or graph replay) draws from the next Philox offset
     }
 }
 
 extern "C" int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
-                            const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta, const int32_t* anchor_idx,
+                            const int32_t* valid_list, const int32_t* hard_list, int32_t* meta, const int32_t* anchor_idx,
                             const int32_t* neg_idx, uint64_t seed, uint64_t offset, uint64_t* step_counter, int N, int C, int D, int Q,
                             int Nn, float temp, float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream) {
     CSS_CHECK_ARG(rows && norms && proto_hat && class_cdf && valid_list && hard_list && meta && loss_kq && anchor_px && loss,
@@ -486,19 +497,18 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
     CSS_CHECK_ARG(Q <= 65535 * 32768, CSS_E_SIZE, "css_score_ce: Q too large");
     if (int e = css_check_dims(C, D)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    draw_offset_kernel<<<1, 1, 0, st>>>(offset, (unsigned long long*)step_counter, meta);
     dim3 grid(Q, C);
     if (grad_anchor)
         score_ce_kernel<true, false, true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
-                                                          valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset,
-                                                          (const unsigned long long*)step_counter, N, Q, Nn,
+                                                          valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                           temp, loss_kq, anchor_px, (float4*)grad_anchor);
     else
         score_ce_kernel<false, true, false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
-                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset,
-                                                          (const unsigned long long*)step_counter, N, Q, Nn,
+                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
                                                            temp, loss_kq, anchor_px, nullptr);
-    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss, (unsigned long long*)step_counter);
-    CSS_CHECK_LAUNCH("css_score_ce", 2);
+    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);
+    CSS_CHECK_LAUNCH("css_score_ce", 3);
     return 0;
 }
 

@@ -32,6 +32,7 @@ def install(reference_root=None, stub_shutup=True):
         # resolved through the reference module at call time, exactly like ddp_model.py:6,121,127,132 does
         setattr(h, name, (lambda n: (lambda *a, **k: getattr(ref_model, n)(*a, **k)))(name))
     ref_loss.Contrast_Loss = _loss.Contrast_Loss
+    ref_loss.Attention_Threshold_Loss = _loss.Attention_Threshold_Loss
     ref_model.Model_ori_pseudo = _models.Model_ori_pseudo
     ref_model.Model_mix = _models.Model_mix
     ref_model.Model_cross = _models.Model_cross

@@ -223,3 +223,54 @@ class Contrast_Loss(nn.Module):
             check(lib.css_sample(ptr(ws.meta), ptr(ws.class_cdf), int(seed), int(offset), C, self.num_queries,
                                  self.num_negatives, ptr(a), ptr(n), stream_ptr()), "css_sample")
         return a, n
+
+
+class _AttentionThresholdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, label, conf, threshold):
+        lib = _lib.load()
+        B, C, H, W = pred.shape
+        dev = pred.device
+        nblk = lib.css_atl_blocks(H, W)
+        lse = torch.empty(B * H * W, device=dev, dtype=torch.float32)
+        partials = torch.empty(B * nblk, device=dev, dtype=torch.float32)
+        counts = torch.empty(3 * B, device=dev, dtype=torch.int32)
+        scale = torch.empty(B, device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        check(lib.css_atl_forward(ptr(pred), ptr(label), ptr(conf), float(threshold), B, C, H, W, ptr(lse), ptr(partials), ptr(counts),
+                                  ptr(scale), ptr(loss), stream_ptr()), "css_atl_forward")
+        ctx.save_for_backward(pred, label, lse, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pred, label, lse, scale = ctx.saved_tensors
+        lib = _lib.load()
+        B, C, H, W = pred.shape
+        grad_pred = torch.empty_like(pred)
+        go = grad_out.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(pred.device):
+            check(lib.css_atl_backward(ptr(go), ptr(pred), ptr(label), ptr(lse), ptr(scale), B, C, H, W, ptr(grad_pred), stream_ptr()),
+                  "css_atl_backward")
+        return grad_pred, None, None, None
+
+
+class Attention_Threshold_Loss(nn.Module):
+    """Drop-in for generalframeworks/loss/loss.py:48-64 (same constructor and forward), SURVEY.md 8(f)-3: one fused forward
+    pass over the logits (+ one backward pass) instead of ~6 passes over [B,C,H,W] tensors and a masked_select."""
+
+    def __init__(self, strong_threshold):
+        super().__init__()
+        self.strong_threshold = strong_threshold
+
+    def forward(self, pred: torch.Tensor, pseudo_label: torch.Tensor, logits: torch.Tensor):
+        if not (pred.is_cuda and pseudo_label.is_cuda and logits.is_cuda):
+            raise RuntimeError("css_b200: Attention_Threshold_Loss needs CUDA tensors (no CPU fallback)")
+        if pred.dtype != torch.float32:
+            raise RuntimeError(f"css_b200: pred must be float32, got {pred.dtype}")
+        if pred.dim() != 4 or pseudo_label.shape != (pred.shape[0],) + tuple(pred.shape[2:]) or logits.shape != pseudo_label.shape:
+            raise RuntimeError("css_b200: pred must be [B,C,H,W], pseudo_label and logits [B,H,W]")
+        pred_c = pred if pred.is_contiguous() else pred.contiguous()
+        with torch.cuda.device(pred.device):
+            return _AttentionThresholdFn.apply(pred_c, pseudo_label.long().contiguous(), logits.float().contiguous(),
+                                               self.strong_threshold)

@@ -55,6 +55,7 @@ extern "C" {
 #define CSS_META_CLS_OF_SLOT  96     /* [32] class id of the k-th present class (increasing)      */
 #define CSS_META_SLOT_OF_CLS  128    /* [32] slot of a class, -1 when absent                      */
 #define CSS_META_TICKET       160    /* internal: last-CTA election of the scan kernel            */
+#define CSS_META_DRAW_OFFSET  162    /* [2] lo/hi words of the Philox offset used by the last css_score_ce */
 
 int         css_version(void);
 const char* css_last_error(void);
@@ -144,13 +145,14 @@ int css_sample(const int32_t* meta, const float* class_cdf, uint64_t seed, uint6
  * Replaces loss.py:124-149 and its autograd backward up to the anchor rows.  rows / norms come from css_rep_pass.
  *   anchor_idx / neg_idx: as produced by css_sample or recorded from the reference; NULL = draw on the fly with
  *   (seed, offset + *step_counter), bit-identical to css_sample with the same (seed, offset).
- *   step_counter: optional DEVICE u64, read as an offset increment and incremented by one at the end of the call, so that
- *   replays of a captured CUDA graph keep drawing fresh samples; NULL = use `offset` alone.
+ *   step_counter: optional DEVICE u64, read as an offset increment and incremented by one by the call, so that replays of a
+ *   captured CUDA graph keep drawing fresh samples; NULL = use `offset` alone.  The offset actually used is left in
+ *   meta[CSS_META_DRAW_OFFSET..+1].
  *   loss_kq f32[C*Q], anchor_px i32[C*Q] (pixel id of each anchor, -1 if none), grad_anchor f32[C*Q*D] or NULL,
  *   loss f32[1] = (1/V) sum_k (1/Q) sum_q loss_kq, exactly 0 when V <= 1.
  */
 int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
-                 const int32_t* valid_list, const int32_t* hard_list, const int32_t* meta,
+                 const int32_t* valid_list, const int32_t* hard_list, int32_t* meta,
                  const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset, uint64_t* step_counter,
                  int N, int C, int D, int Q, int Nn, float temp,
                  float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream);
@@ -171,6 +173,18 @@ int css_grad_scatter(const float* grad_out, const int32_t* anchor_px, const floa
 int css_threshold_glue(const int64_t* label_l, const int64_t* label_u, const float* conf_u, float weak_threshold,
                        int mode, int B, int C, int H, int W, int h, int w,
                        float* label_all, float* mask_all, void* stream);
+
+/* ---- Attention_Threshold_Loss ------------------------------------------------------------------------------
+ * out = mean over {p : CE_p > 0} of w_b * CE(pred[:,p], label_p), w_b = #(conf_b >= threshold) / #(label_b >= 0); label -1 is
+ * ignored.  Replaces loss.py:48-64 (forward) and its autograd backward.
+ *   pred [B,C,H,W] f32, label [B,H,W] i64, conf [B,H,W] f32
+ *   lse f32[B*H*W] (saved for backward), partials f32[B * css_atl_blocks(H,W)], counts i32[3*B], scale f32[B] (saved), loss f32[1]
+ */
+int css_atl_blocks(int H, int W);
+int css_atl_forward(const float* pred, const int64_t* label, const float* conf, float threshold, int B, int C, int H, int W,
+                    float* lse, float* partials, int32_t* counts, float* scale, float* loss, void* stream);
+int css_atl_backward(const float* grad_out, const float* pred, const int64_t* label, const float* lse, const float* scale,
+                     int B, int C, int H, int W, float* grad_pred, void* stream);
 
 #ifdef __cplusplus
 }

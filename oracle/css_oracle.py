@@ -357,3 +357,36 @@ def contrast_loss(rep, label, mask, prob, prototypes, *, num_queries, num_negati
         grad = np.ascontiguousarray(grad_rows.reshape(B2, h, w, D).transpose(0, 3, 1, 2))
     info["proto_rep"] = proto_rep
     return loss, grad, info
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY.md 8(f)-3 : Attention_Threshold_Loss (logit-space unsupervised loss)
+# --------------------------------------------------------------------------------------
+def attention_threshold_loss(pred, pseudo_label, logits, strong_threshold, want_grad=True):
+    """generalframeworks/loss/loss.py:53-64 and the gradient autograd gives for it.
+    pred [B,C,H,W] f32, pseudo_label [B,H,W] int (-1 = ignore), logits [B,H,W] f32 (confidences)."""
+    pred = np.asarray(pred, dtype=f32)
+    lab = np.asarray(pseudo_label, dtype=np.int64)
+    conf = np.asarray(logits, dtype=f32)
+    B, C, H, W = pred.shape
+    valid = lab >= 0                                                                      # :55
+    weighting = ((conf.reshape(B, -1) >= f32(strong_threshold)).sum(-1).astype(f32)
+                 / valid.reshape(B, -1).sum(-1).astype(f32)).astype(f32)                  # :56
+    m = pred.max(axis=1, keepdims=True)
+    e = np.exp((pred - m).astype(f32)).astype(f32)
+    ssum = e.sum(axis=1, keepdims=True, dtype=f32)
+    lse = (m + np.log(ssum))[:, 0].astype(f32)
+    picked = np.take_along_axis(pred, np.maximum(lab, 0)[:, None], axis=1)[:, 0]
+    loss = np.where(valid, lse - picked, f32(0)).astype(f32)                              # :59 (ignore_index=-1 -> 0)
+    sel = loss > 0                                                                        # :60
+    out = np.mean((weighting[:, None, None] * loss)[sel], dtype=f32) if sel.any() else f32(np.nan)
+    grad = None
+    if want_grad:
+        n = f32(sel.sum())
+        soft = (e / ssum).astype(f32)
+        onehot = np.zeros_like(pred)
+        np.put_along_axis(onehot, np.maximum(lab, 0)[:, None], f32(1), axis=1)
+        # unselected pixels get exactly 0 (also when their image's weighting is nan: nll_loss backward skips ignored targets)
+        coef = np.where(sel, (weighting[:, None, None] / n).astype(f32), f32(0))
+        grad = ((soft - onehot) * coef[:, None]).astype(f32)
+    return f32(out), grad

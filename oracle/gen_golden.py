@@ -160,6 +160,22 @@ def glue_case(name, *, strategy, B, C, H, W, h, w, weak, seed):
     print(f"  {name}: ok")
 
 
+def atl_case(name, *, B, C, H, W, thr, seed):
+    """Attention_Threshold_Loss forward + backward of the reference (loss.py:48-64)."""
+    L, M, U = load_reference()
+    g = synth._gen(seed)
+    cls = synth.class_map(B, C, H, W, g, ignore_frac=0.15, block=6)
+    pred = synth.logits_for(cls, C, g).requires_grad_(True)
+    conf = torch.floor(torch.rand(B, H, W, generator=g) * 255) / 255
+    cls[0, :2] = -1
+    crit = L.Attention_Threshold_Loss(strong_threshold=thr)
+    loss = crit(pred, cls, conf)
+    (loss * 1.7).backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), C=C, thr=thr, pred=_np(pred), label=_np(cls).astype(np.int16), conf=_np(conf),
+                        loss=np.float32(loss.item()), grad=_np(pred.grad), grad_scale=np.float32(1.7))
+    print(f"  {name}: loss={loss.item():.6f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     D = 256
@@ -195,6 +211,10 @@ def main():
     stage12_case("stage12_mix_c21", kind="mix", B=2, C=21, h=9, w=9, H=33, W=33, temp=0.5, seed=61, zero_rows=(5,))
     stage12_case("stage12_cross_c19", kind="cross", B=1, C=19, h=7, w=10, H=25, W=37, temp=0.5, seed=67)
     stage12_case("stage12_ori_c21", kind="ori", B=2, C=21, h=9, w=9, H=33, W=33, temp=0.5, seed=71)
+
+    print("attention-threshold loss cases")
+    atl_case("atl_c21", B=3, C=21, H=23, W=19, thr=0.7, seed=91)
+    atl_case("atl_c19", B=2, C=19, H=16, W=33, thr=0.97, seed=93)
 
     print("glue cases")
     glue_case("glue_mix", strategy="mix", B=2, C=21, H=33, W=33, h=9, w=9, weak=0.7, seed=81)

@@ -71,3 +71,27 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_score_kernel_issues_all_row_loads_before_the_fmas():
+    """Performance guard that needs no GPU: in the gradient variant of the scorer the eight 128-bit loads of a candidate
+    row must be issued back to back.  Under a tighter register budget ptxas sinks the last load below the first FFMA2s and
+    the row latency is paid twice per step (measured: 264 -> 332 us); this pins the schedule the timings were taken with."""
+    import shutil
+    import subprocess
+    from css_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    m = re.search(r"Function : (\S*score_ce_kernelILb1E\S*)\n(.*?)(?=Function : |\Z)", sass, flags=re.S)
+    assert m, "gradient variant of score_ce_kernel not found"
+    ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", m.group(2), flags=re.M)
+    best = run = 0
+    for op in ops:
+        if op.startswith("LDG.E.128"):
+            run += 1
+            best = max(best, run)
+        elif op.startswith(("FFMA2", "LDS")):
+            run = 0
+    assert best >= 8, f"row loads are split by compute (longest run of LDG.E.128 = {best})"
+    assert any(op.startswith("FFMA2") for op in ops), "packed fp32x2 FMAs (sm_100 FFMA2) expected in the scorer"

@@ -103,6 +103,14 @@ def main():
     cu = torch.rand(B, H, W, generator=g0).to(dev)
     res["threshold_glue K0 (8(f)-1, not in path sum)"] = timeit(
         lambda i: css_b200.ops.threshold_glue(ll, lu, cu, 0.7, C, (h, w), "mix" if cfg["strategy"] == "mix" else "ori"), a.iters)
+    atl = css_b200.Attention_Threshold_Loss(0.97).cuda()
+    pl = torch.randn(B, C, H, W, generator=g0).to(dev)
+
+    def atl_step(i):
+        pp_ = pl.detach().requires_grad_(True)
+        (gr,) = torch.autograd.grad(atl(pp_, lu, cu), pp_)
+
+    res["attention_threshold_loss fwd+bwd (8(f)-3, not in path sum)"] = timeit(atl_step, a.iters)
     res["select (3 kernels)"] = timeit(select, a.iters)
     res["class_stats (+reduce)"] = timeit(stream, a.iters)
     res["rep_rows only (ori flow)"] = timeit(lambda i: css_b200.ops.rep_rows(rep_all[i % P]), a.iters)
@@ -110,9 +118,10 @@ def main():
     res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
     res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
     res["grad_scatter (+memset)"] = timeit(scatter, a.iters)
-    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)", "threshold_glue K0 (8(f)-1, not in path sum)"))
+    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)", "threshold_glue K0 (8(f)-1, not in path sum)",
+                                            "attention_threshold_loss fwd+bwd (8(f)-3, not in path sum)"))
     for k, v in res.items():
-        print(f"{k:46s} {v:9.1f} us")
+        print(f"{k:60s} {v:9.1f} us")
     print(f"{'sum (path)':34s} {tot:9.1f} us")
     print(json.dumps({"workload": a.workload, "us": res}))
 
