@@ -11,6 +11,8 @@
 #define ATL_THREADS 256
 
 // counts layout per image: [0] #(loss > 0), [1] #(conf >= thr), [2] #(label >= 0)
+// CT > 0: compile-time class count (the C logits of a pixel stay in registers: pred is read exactly once); CT == 0: any C.
+template <int CT>
 __global__ void __launch_bounds__(ATL_THREADS) atl_forward_kernel(const float* __restrict__ pred, const int64_t* __restrict__ label,
                                                                   const float* __restrict__ conf, float thr, int C, int HW,
                                                                   float* __restrict__ lse_out, float* __restrict__ partials,
@@ -24,14 +26,32 @@ __global__ void __launch_bounds__(ATL_THREADS) atl_forward_kernel(const float* _
     if (p < HW) {
         const float* x = pred + (size_t)b * C * HW + p;
         const long long lab = label[(size_t)b * HW + p];
-        float m = -INFINITY;
-        for (int c = 0; c < C; ++c) m = fmaxf(m, ldg_stream(x + (size_t)c * HW));
-        float s = 0.f;
-        for (int c = 0; c < C; ++c) s += expf(__ldg(x + (size_t)c * HW) - m);
-        const float lse = m + logf(s);
+        float lse, picked = 0.f;
+        if (CT > 0) {
+            float v[CT > 0 ? CT : 1];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] = ldg_stream(x + (size_t)c * HW);
+            float m = v[0];
+#pragma unroll
+            for (int c = 1; c < CT; ++c) m = fmaxf(m, v[c]);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                s += expf(v[c] - m);
+                if (c == lab) picked = v[c];
+            }
+            lse = m + logf(s);
+        } else {
+            float m = -INFINITY;
+            for (int c = 0; c < C; ++c) m = fmaxf(m, __ldg(x + (size_t)c * HW));
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s += expf(__ldg(x + (size_t)c * HW) - m);
+            lse = m + logf(s);
+            if (lab >= 0 && lab < C) picked = __ldg(x + (size_t)lab * HW);
+        }
         lse_out[(size_t)b * HW + p] = lse;
         valid = lab >= 0;
-        if (valid && lab < C) loss = lse - __ldg(x + (size_t)lab * HW);
+        if (valid && lab < C) loss = lse - picked;
         pos = loss > 0.f;
         if (!pos) loss = 0.f;
         hi = conf[(size_t)b * HW + p] >= thr;
@@ -89,6 +109,7 @@ __global__ void __launch_bounds__(256) atl_finalize_kernel(const float* __restri
     }
 }
 
+template <int CT>
 __global__ void __launch_bounds__(ATL_THREADS) atl_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ pred,
                                                                    const int64_t* __restrict__ label, const float* __restrict__ lse,
                                                                    const float* __restrict__ scale, int C, int HW,
@@ -99,13 +120,27 @@ __global__ void __launch_bounds__(ATL_THREADS) atl_backward_kernel(const float* 
     float* g = grad_pred + (size_t)b * C * HW + p;
     const long long lab = label[(size_t)b * HW + p];
     const float l = lse[(size_t)b * HW + p];
-    bool on = lab >= 0 && lab < C;
-    if (on) on = (l - __ldg(x + (size_t)lab * HW)) > 0.f;     // masked_select(loss > 0): no gradient elsewhere
+    const bool labelled = lab >= 0 && lab < C;
+    const float k = __ldg(grad_out) * scale[b];
+    if (CT > 0) {
+        float v[CT > 0 ? CT : 1];
+        float picked = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            v[c] = labelled ? ldg_stream(x + (size_t)c * HW) : 0.f;
+            if (c == lab) picked = v[c];
+        }
+        const bool on = labelled && (l - picked) > 0.f;       // masked_select(loss > 0): no gradient elsewhere
+#pragma unroll
+        for (int c = 0; c < CT; ++c) g[(size_t)c * HW] = on ? k * (expf(v[c] - l) - (c == lab ? 1.f : 0.f)) : 0.f;
+        return;
+    }
+    bool on = labelled;
+    if (on) on = (l - __ldg(x + (size_t)lab * HW)) > 0.f;
     if (!on) {
         for (int c = 0; c < C; ++c) g[(size_t)c * HW] = 0.f;
         return;
     }
-    const float k = __ldg(grad_out) * scale[b];
     for (int c = 0; c < C; ++c) {
         const float sm = expf(ldg_stream(x + (size_t)c * HW) - l);
         g[(size_t)c * HW] = k * (sm - (c == lab ? 1.f : 0.f));
@@ -123,7 +158,9 @@ extern "C" int css_atl_forward(const float* pred, const int64_t* label, const fl
     const int HW = H * W, nblk = css_atl_blocks(H, W);
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * B, st);
     if (e != cudaSuccess) { css_set_error("css_atl_forward: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    atl_forward_kernel<<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
+    if (C == 21) atl_forward_kernel<21><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
+    else if (C == 19) atl_forward_kernel<19><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
+    else atl_forward_kernel<0><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
     atl_finalize_kernel<<<1, 256, 0, st>>>(partials, counts, B, nblk, scale, loss);
     CSS_CHECK_LAUNCH("css_atl_forward", 2);
     return 0;
@@ -134,8 +171,11 @@ extern "C" int css_atl_backward(const float* grad_out, const float* pred, const 
     CSS_CHECK_ARG(grad_out && pred && label && lse && scale && grad_pred, CSS_E_ARG, "css_atl_backward: null pointer");
     CSS_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, CSS_E_ARG, "css_atl_backward: bad size");
     const int HW = H * W;
-    atl_backward_kernel<<<dim3(css_atl_blocks(H, W), B), ATL_THREADS, 0, (cudaStream_t)stream>>>(grad_out, pred, label, lse, scale, C, HW,
-                                                                                                grad_pred);
+    const dim3 grid(css_atl_blocks(H, W), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 21) atl_backward_kernel<21><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
+    else if (C == 19) atl_backward_kernel<19><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
+    else atl_backward_kernel<0><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
     CSS_CHECK_LAUNCH("css_atl_backward", 1);
     return 0;
 }
