@@ -186,10 +186,13 @@ struct Online {            // online softmax state (base 2) of one 8-lane group
     float4 acc[8];
 };
 
-// `inv_nr` = 1 / max(||r||, 1e-8): the rows are stored raw, the state accumulates sum_j 2^{z_j-m} r_j / ||r_j||
-template <bool WANT_GRAD>
+// `inv_nr` = 1 / max(||r||, 1e-8): the rows are stored raw, the state accumulates sum_j 2^{z_j-m} r_j / ||r_j||.
+// FIX: cos <= 1, so m = scale2 = log2(e)/temp bounds every logit from above; with that fixed reference no running max, no
+// rescaling and no data-dependent branch are needed (used whenever 2^(-2 scale2) is comfortably inside fp32, i.e. temp > 0.024;
+// smaller temperatures take the online-max path).
+template <bool WANT_GRAD, bool FIX>
 __device__ __forceinline__ void online_update(Online& st, float z, bool valid, float inv_nr, const float4 (&r)[8]) {
-    if (valid && z > st.m) {                       // group-uniform; rare after the first few rows
+    if (!FIX && valid && z > st.m) {               // group-uniform; rare after the first few rows
         const float sc = exp2f(st.m - z);          // m = -inf -> 0
         st.l *= sc;
         if (WANT_GRAD) {
@@ -339,7 +342,7 @@ __global__ void draw_offset_kernel(uint64_t offset, unsigned long long* __restri
     meta[CSS_META_DRAW_OFFSET + 1] = (int32_t)(uint32_t)(o >> 32);
 }
 
-template <bool WANT_GRAD, bool PREFETCH, bool ASMEM>
+template <bool WANT_GRAD, bool PREFETCH, bool ASMEM, bool FIX>
 __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) score_ce_kernel(
     const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     const float scale2 = 1.4426950408889634f / temp;          // logits in base 2: z2 = cos * log2(e) / temp
 
     Online st;
-    st.m = -INFINITY;
+    st.m = FIX ? scale2 : -INFINITY;                  // FIX: cos <= 1 bounds every logit by scale2
     st.l = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) st.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
                     z0 = z;
                     cos_pos = cosv;
                 }
-                online_update<WANT_GRAD>(st, z, row != -2, inv, r);
+                online_update<WANT_GRAD, FIX>(st, z, row != -2, inv, r);
             }
         } else {
 #pragma unroll 1
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
                     z0 = z;
                     cos_pos = cosv;
                 }
-                online_update<WANT_GRAD>(st, z, row != -2, inv, r);
+                online_update<WANT_GRAD, FIX>(st, z, row != -2, inv, r);
             }
         }
     }
@@ -499,14 +502,18 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     draw_offset_kernel<<<1, 1, 0, st>>>(offset, (unsigned long long*)step_counter, meta);
     dim3 grid(Q, C);
-    if (grad_anchor)
-        score_ce_kernel<true, false, true><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
-                                                          valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
-                                                          temp, loss_kq, anchor_px, (float4*)grad_anchor);
-    else
-        score_ce_kernel<false, true, false><<<grid, SC_THREADS, 0, st>>>((const float4*)rows, norms, (const float4*)proto_hat, class_cdf,
-                                                           valid_list, hard_list, meta, anchor_idx, neg_idx, seed, offset, N, Q, Nn,
-                                                           temp, loss_kq, anchor_px, nullptr);
+    // fixed-reference softmax whenever 2^(-2 log2(e)/temp) is far from fp32 underflow (temp > ~0.024); online max otherwise
+    const bool fix = (2.f * 1.4426950408889634f / temp) < 120.f;
+#define SC_ARGS (const float4*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, meta, anchor_idx, neg_idx, seed, \
+                offset, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
+    if (grad_anchor) {
+        if (fix) score_ce_kernel<true, false, true, true><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
+        else score_ce_kernel<true, false, true, false><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
+    } else {
+        if (fix) score_ce_kernel<false, true, false, true><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
+        else score_ce_kernel<false, true, false, false><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
+    }
+#undef SC_ARGS
     loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);
     CSS_CHECK_LAUNCH("css_score_ce", 3);
     return 0;

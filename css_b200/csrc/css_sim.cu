@@ -314,16 +314,15 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
         }
     }
     float sum = 0.f;
-    float emax = 0.f;
 #pragma unroll
     for (int c = 0; c < CN; ++c) {
         if (CT > 0 || c < C) {
             v[c] = ex2_approx((v[c] - m) * 1.4426950408889634f);   // exp(x - m): exactly 1 for the arg-max, monotone elsewhere
             sum += v[c];
-            emax = fmaxf(emax, v[c]);
         }
     }
-    // torch.max(softmax): the largest e_c/sum, first index on ties (ties after rounding included)
+    // torch.max(softmax): the largest e_c/sum is e = 1 (the arg-max); first index on ties (ties after rounding included)
+    const float emax = 1.f;
     int lab = 0;
 #pragma unroll
     for (int c = CN - 1; c >= 0; --c)

@@ -83,15 +83,16 @@ def test_score_kernel_issues_all_row_loads_before_the_fmas():
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
-    m = re.search(r"Function : (\S*score_ce_kernelILb1E\S*)\n(.*?)(?=Function : |\Z)", sass, flags=re.S)
-    assert m, "gradient variant of score_ce_kernel not found"
-    ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", m.group(2), flags=re.M)
-    best = run = 0
-    for op in ops:
-        if op.startswith("LDG.E.128"):
-            run += 1
-            best = max(best, run)
-        elif op.startswith(("FFMA2", "LDS")):
-            run = 0
-    assert best >= 8, f"row loads are split by compute (longest run of LDG.E.128 = {best})"
-    assert any(op.startswith("FFMA2") for op in ops), "packed fp32x2 FMAs (sm_100 FFMA2) expected in the scorer"
+    funcs = re.findall(r"Function : (\S*score_ce_kernelILb1E\S*)\n(.*?)(?=Function : |\Z)", sass, flags=re.S)
+    assert funcs, "gradient variants of score_ce_kernel not found"
+    for name, body in funcs:
+        ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body, flags=re.M)
+        best = run = 0
+        for op in ops:
+            if op.startswith("LDG.E.128"):
+                run += 1
+                best = max(best, run)
+            elif op.startswith(("FFMA2", "LDS")):
+                run = 0
+        assert best >= 8, f"{name}: row loads are split by compute (longest run of LDG.E.128 = {best})"
+        assert any(op.startswith("FFMA2") for op in ops), "packed fp32x2 FMAs (sm_100 FFMA2) expected in the scorer"

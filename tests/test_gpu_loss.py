@@ -377,3 +377,27 @@ def test_cuda_graph_replays_draw_fresh_samples():
         losses2.append(l2.item())
     assert losses2[2:] == [s[0] for s in seen]
     assert torch.equal(protos2, protos)
+
+
+@pytest.mark.parametrize("temp", [0.02, 0.1])
+def test_small_temperatures_online_max_path(temp):
+    """temp = 0.02 takes the online-max softmax path of the scorer (fixed-reference softmax is only used while
+    2^(-2 log2(e)/temp) is far from fp32 underflow); both must match the oracle."""
+    import css_b200
+    from css_b200 import synth
+    B2, C, h, w, Q, Nn = 2, 9, 20, 18, 16, 40
+    d = synth.student_batch(B2, C, h, w, seed=31, block=3)
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=0.97, alpha=0.99)
+    crit = css_b200.Contrast_Loss(seed=5, **kw).cuda()
+    rep, label, mask, prob = (d[k].numpy() for k in ("rep", "label", "mask", "prob"))
+    protos0 = synth.warm_prototypes(C, seed=8)
+    protos = protos0.clone().cuda()
+    loss, grad = run_gpu(crit, rep, label, mask, prob, protos)
+    sel = crit.selection()
+    a, n = crit.sample_indices(5, 0)
+    slots = scored_slots(sel)
+    sampler = O.RecordedDraws([a.cpu().numpy()[k] for k in slots], [n.cpu().numpy()[k].reshape(-1) for k in slots])
+    p_or = protos0.numpy().copy()
+    l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=sampler, **kw)
+    np.testing.assert_allclose(loss.item(), l_or, rtol=RTOL)
+    np.testing.assert_allclose(grad.cpu().numpy(), g_or, rtol=RTOL, atol=1e-6 * np.abs(g_or).max())
