@@ -31,10 +31,10 @@ SIGNATURES = {
     "css_select": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "css_rep_pass": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P]),
     "css_class_blocks": (c_int, [c_int]),
-    "css_class_stats": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "css_class_stats": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
     "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, P, P, P]),
     "css_sample": (c_int, [P, P, c_uint64, c_uint64, c_int, c_int, c_int, P, P, P]),
-    "css_score_ce": (c_int, [P, P, P, P, P, P, P, P, P, c_uint64, c_uint64, P, c_int, c_int, c_int, c_int, c_int, c_float,
+    "css_score_ce": (c_int, [P, c_int, P, P, P, P, P, P, P, P, c_uint64, c_uint64, P, c_int, c_int, c_int, c_int, c_int, c_float,
                              P, P, P, P, P]),
     "css_grad_scatter": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "css_atl_blocks": (c_int, [c_int, c_int]),

@@ -60,6 +60,19 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     return v;
 }
 
+// Pixel-major rows are stored in the representation map's own dtype (fp32, or bf16 = lossless for a bf16 map and half the
+// gather bytes).  row_f4(rows, row, q) returns elements 4q..4q+3 of a row widened to fp32.
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 row_f4(const float* rows, size_t row, int q) {
+    return __ldg(reinterpret_cast<const float4*>(rows) + row * (CSS_D / 4) + q);
+}
+__device__ __forceinline__ float4 row_f4(const __nv_bfloat16* rows, size_t row, int q) {
+    return bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(rows) + row * (CSS_D / 4) + q));
+}
+
 // Philox4x32-10 (Salmon et al., SC'11), the counter-based generator the device sampler is built on.
 struct Philox {
     static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -227,8 +227,8 @@ struct QueryShared {                     // per-CTA scratch for merging the SC_W
 
 // Merge the four 8-lane groups of every warp, then the SC_WARPS warps (fixed order), and write the query's loss, anchor
 // pixel and d loss / d anchor.
-template <bool WANT_GRAD>
-__device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos, QueryShared& sh, const float4* __restrict__ rows,
+template <bool WANT_GRAD, typename RT>
+__device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos, QueryShared& sh, const RT* __restrict__ rows,
                                              const float4* __restrict__ proto_hat, float inv_na, int pa, int c, int k, int q, int Q,
                                              int V, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
                                              float4* __restrict__ grad_anchor) {
@@ -292,7 +292,6 @@ __device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos
         // dL/da = (sum_j g_j r_hat_j - (sum_j g_j cos_j) a_hat) / max(||a||, eps),  g_j = (pi_j - [j==0]) / (Q V temp)
         // with sum_j pi_j r_hat_j = acc / l and sum_j pi_j cos_j = a_hat . (acc / l)        
         const float inv_l = 1.f / l;
-        const float4* ap = rows + (size_t)pa * (CSS_D / 4);
         const float4* php = proto_hat + (size_t)c * (CSS_D / 4);
         float4 S[2], av[2], ph[2];
         float sdot = 0.f;
@@ -309,7 +308,7 @@ __device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos
                 t.w = fmaf(v.w, sc[w2], t.w);
             }
             S[h2] = make_float4(t.x * inv_l, t.y * inv_l, t.z * inv_l, t.w * inv_l);
-            av[h2] = __ldg(ap + col);                       // raw anchor -> a_hat
+            av[h2] = row_f4(rows, (size_t)pa, col);         // raw anchor -> a_hat
             av[h2].x *= inv_na; av[h2].y *= inv_na; av[h2].z *= inv_na; av[h2].w *= inv_na;
             ph[h2] = __ldg(php + col);
             sdot += S[h2].x * av[h2].x + S[h2].y * av[h2].y + S[h2].z * av[h2].z + S[h2].w * av[h2].w;
@@ -342,9 +341,31 @@ __global__ void draw_offset_kernel(uint64_t offset, unsigned long long* __restri
     meta[CSS_META_DRAW_OFFSET + 1] = (int32_t)(uint32_t)(o >> 32);
 }
 
-template <bool WANT_GRAD, bool PREFETCH, bool ASMEM, bool FIX>
+// candidate row `row` (>= 0: pixel-major row of the map, widened to fp32; < 0: the fp32 prototype row `pp`) -> r[0..7]
+template <typename RT>
+__device__ __forceinline__ void load_candidate(const RT* __restrict__ rows, const float4* __restrict__ pp, int row, int l8, float4 (&r)[8]) {
+    if constexpr (sizeof(RT) == 4) {
+        const float4* p = (row >= 0) ? reinterpret_cast<const float4*>(rows) + (size_t)row * (CSS_D / 4) + l8 : pp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
+    } else {
+        if (row >= 0) {                                    // group-uniform branch
+            const uint2* p = reinterpret_cast<const uint2*>(rows) + (size_t)row * (CSS_D / 4) + l8;
+            uint2 u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = __ldg(p + i * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = bf16x4_to_f4(u[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = __ldg(pp + i * 8);
+        }
+    }
+}
+
+template <bool WANT_GRAD, bool PREFETCH, bool ASMEM, bool FIX, typename RT>
 __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) score_ce_kernel(
-    const float4* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
+    const RT* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
     uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
@@ -372,12 +393,11 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     __shared__ float4 s_a[ASMEM ? CSS_D / 4 : 1];
     float4 a[ASMEM ? 1 : 8];
     if (ASMEM) {
-        if (threadIdx.x < CSS_D / 4) s_a[threadIdx.x] = __ldg(rows + (size_t)pa * (CSS_D / 4) + threadIdx.x);
+        if (threadIdx.x < CSS_D / 4) s_a[threadIdx.x] = row_f4(rows, (size_t)pa, threadIdx.x);
         __syncthreads();
     } else {
-        const float4* ap = rows + (size_t)pa * (CSS_D / 4) + l8;
 #pragma unroll
-        for (int i = 0; i < (ASMEM ? 1 : 8); ++i) a[i] = __ldg(ap + i * 8);
+        for (int i = 0; i < (ASMEM ? 1 : 8); ++i) a[i] = row_f4(rows, (size_t)pa, i * 8 + l8);
     }
     const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(&s_a[ASMEM ? l8 : 0]);
     const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);       // cosine_similarity eps (loss.py:146)
@@ -421,11 +441,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
             // software pipeline: the next candidate row is in flight while the current one is scored
             float4 rn[8];
             int row_n = __shfl_sync(0xffffffffu, my_row, grp);
-            {
-                const float4* p = (row_n >= 0) ? rows + (size_t)row_n * (CSS_D / 4) + l8 : pp;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rn[i] = __ldg(p + i * 8);
-            }
+            load_candidate(rows, pp, row_n, l8, rn);
 #pragma unroll 1
             for (int t = 0; t < steps; ++t) {
                 float4 r[8];
@@ -434,11 +450,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
                 const int row = row_n;
                 const float inv = __shfl_sync(0xffffffffu, my_inv, t * 4 + grp);
                 row_n = __shfl_sync(0xffffffffu, my_row, ((t + 1) & 7) * 4 + grp);
-                if (t + 1 < steps) {
-                    const float4* p = (row_n >= 0) ? rows + (size_t)row_n * (CSS_D / 4) + l8 : pp;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rn[i] = __ldg(p + i * 8);
-                }
+                if (t + 1 < steps) load_candidate(rows, pp, row_n, l8, rn);
                 const float cosv = group_sum8(score_dot<ASMEM>(a, a_addr, r)) * (inv_na * inv);
                 const float z = cosv * scale2;
                 if (row == -1) {
@@ -452,10 +464,8 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
             for (int t = 0; t < steps; ++t) {
                 const int row = __shfl_sync(0xffffffffu, my_row, t * 4 + grp);
                 const float inv = __shfl_sync(0xffffffffu, my_inv, t * 4 + grp);
-                const float4* p = (row >= 0) ? rows + (size_t)row * (CSS_D / 4) + l8 : pp;
                 float4 r[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
+                load_candidate(rows, pp, row, l8, r);
                 const float cosv = group_sum8(score_dot<ASMEM>(a, a_addr, r)) * (inv_na * inv);
                 const float z = cosv * scale2;
                 if (row == -1) {
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
         }
     }
 
-    finish_query<WANT_GRAD>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
+    finish_query<WANT_GRAD, RT>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
 }
 
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
     }
 }
 
-extern "C" int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
+extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms, const float* proto_hat, const float* class_cdf,
                             const int32_t* valid_list, const int32_t* hard_list, int32_t* meta, const int32_t* anchor_idx,
                             const int32_t* neg_idx, uint64_t seed, uint64_t offset, uint64_t* step_counter, int N, int C, int D, int Q,
                             int Nn, float temp, float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream) {
@@ -497,6 +507,7 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
     CSS_CHECK_ARG((anchor_idx == nullptr) == (neg_idx == nullptr), CSS_E_ARG,
                   "css_score_ce: anchor_idx and neg_idx must be fed together");
     CSS_CHECK_ARG(N > 0 && Q > 0 && Nn > 0 && Q < (1 << 24), CSS_E_ARG, "css_score_ce: bad N/Q/Nn");
+    CSS_CHECK_ARG(rows_dtype == CSS_DTYPE_F32 || rows_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_score_ce: rows dtype %d", rows_dtype);
     CSS_CHECK_ARG(Q <= 65535 * 32768, CSS_E_SIZE, "css_score_ce: Q too large");
     if (int e = css_check_dims(C, D)) return e;
     cudaStream_t st = (cudaStream_t)stream;
@@ -504,15 +515,21 @@ extern "C" int css_score_ce(const float* rows, const float* norms, const float* 
     dim3 grid(Q, C);
     // fixed-reference softmax whenever 2^(-2 log2(e)/temp) is far from fp32 underflow (temp > ~0.024); online max otherwise
     const bool fix = (2.f * 1.4426950408889634f / temp) < 120.f;
-#define SC_ARGS (const float4*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, meta, anchor_idx, neg_idx, seed, \
-                offset, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
-    if (grad_anchor) {
-        if (fix) score_ce_kernel<true, false, true, true><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
-        else score_ce_kernel<true, false, true, false><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
-    } else {
-        if (fix) score_ce_kernel<false, true, false, true><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
-        else score_ce_kernel<false, true, false, false><<<grid, SC_THREADS, 0, st>>>(SC_ARGS);
-    }
+#define SC_ARGS(RT_) (const RT_*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, meta, anchor_idx, neg_idx, seed, \
+                     offset, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
+#define SC_RUN(RT_)                                                                                                 \
+    do {                                                                                                            \
+        if (grad_anchor) {                                                                                          \
+            if (fix) score_ce_kernel<true, false, true, true, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));         \
+            else score_ce_kernel<true, false, true, false, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));           \
+        } else {                                                                                                    \
+            if (fix) score_ce_kernel<false, sizeof(RT_) == 4, false, true, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));       \
+            else score_ce_kernel<false, sizeof(RT_) == 4, false, false, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));         \
+        }                                                                                                           \
+    } while (0)
+    if (rows_dtype == CSS_DTYPE_F32) SC_RUN(float);
+    else SC_RUN(__nv_bfloat16);
+#undef SC_RUN
 #undef SC_ARGS
     loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);
     CSS_CHECK_LAUNCH("css_score_ce", 3);

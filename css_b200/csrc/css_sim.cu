@@ -60,7 +60,7 @@ __device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) {
 template <int NG, bool ROWS, typename T>
 __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const T* __restrict__ rep, const float* __restrict__ scratch,
                                                                          int hw, int N, int C, int mode, float temp,
-                                                                         float* __restrict__ out, float* __restrict__ rows,
+                                                                         float* __restrict__ out, T* __restrict__ rows,
                                                                          float* __restrict__ norms) {
     constexpr int DS = CSS_D / SM_KS;          // channels per slice
     constexpr int PL = 32 / SM_KS;             // pixel lanes per warp
@@ -104,15 +104,30 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
             for (int u = 0; u < SM_U; ++u)
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) v[u][j] = ld_elem(x[j] + (size_t)(d0 + u) * hw);
-            if (ROWS) {
+            if (ROWS && sizeof(T) == 2) {
+                // bf16 map -> bf16 rows (lossless): the 16 channels a lane holds are 32 contiguous bytes = one whole sector
+#pragma unroll
+                for (int j = 0; j < SM_PPT; ++j) {
+                    if (pix[j] < N) {
+                        uint32_t w[SM_U / 2];
+#pragma unroll
+                        for (int u = 0; u < SM_U; u += 2)
+                            w[u / 2] = (__float_as_uint(v[u][j]) >> 16) | (__float_as_uint(v[u + 1][j]) & 0xffff0000u);
+                        uint4* r = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(rows) + (size_t)pix[j] * CSS_D + ks * DS + d0);
+                        r[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        r[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                }
+            } else if (ROWS) {
                 // Transposed write-out straight from registers.  A lane holds 64 contiguous bytes (16 channels) of its pixel's
                 // row; neighbouring lanes (pixels p, p+1) first swap 16-byte chunks so that every 128-bit store instruction
                 // completes whole 32-byte sectors (lane pair -> one sector) instead of half sectors.
+                float* rows_f = reinterpret_cast<float*>(rows);
                 const int odd = psub & 1;
 #pragma unroll
                 for (int j = 0; j < SM_PPT; ++j) {
                     const int pA = pix[j] - odd, pB = pA + 1;
-                    float* rA = rows + (size_t)pA * CSS_D + ks * DS + d0 + 4 * odd;
+                    float* rA = rows_f + (size_t)pA * CSS_D + ks * DS + d0 + 4 * odd;
                     float* rB = rA + CSS_D;
 #pragma unroll
                     for (int hh = 0; hh < SM_U / 8; ++hh) {
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
 
 template <int NG, bool ROWS, typename T>
 static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
-                            float* rows, float* norms, cudaStream_t st) {
+                            T* rows, float* norms, cudaStream_t st) {
     constexpr int WP = (32 / SM_KS) * SM_PPT;
     const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
     const int cap = css_cached_sm_count() * SM_MINB;
@@ -215,7 +230,7 @@ static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, i
 
 template <bool ROWS, typename T>
 static void dispatch_rep_pass(int ng, const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
-                              float* rows, float* norms, cudaStream_t st) {
+                              T* rows, float* norms, cudaStream_t st) {
     switch (ng) {
         case 1: launch_rep_pass<1, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
         case 2: launch_rep_pass<2, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
@@ -229,7 +244,7 @@ static void dispatch_rep_pass(int ng, const T* rep, const float* scratch, int hw
 }
 
 extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C, int D, int h,
-                            int w, int mode, float temp, float* sim_out, float* rows, float* norms, void* stream) {
+                            int w, int mode, float temp, float* sim_out, void* rows, float* norms, void* stream) {
     const bool want_sim = sim_out != nullptr, want_rows = rows != nullptr;
     CSS_CHECK_ARG(rep && (want_sim || want_rows), CSS_E_ARG, "css_rep_pass: null pointer / nothing to do");
     CSS_CHECK_ARG(!want_sim || (prototypes && proto_scratch), CSS_E_ARG, "css_rep_pass: sim_out needs prototypes and proto_scratch");
@@ -250,9 +265,10 @@ extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototy
 #define REP_PASS_RUN(TYPE)                                                                                                  \
     do {                                                                                                                    \
         const TYPE* r = (const TYPE*)rep;                                                                                   \
-        if (want_sim && want_rows) dispatch_rep_pass<true, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st); \
-        else if (want_sim) dispatch_rep_pass<false, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rows, norms, st);      \
-        else launch_rep_pass<0, true, TYPE>(r, nullptr, hw, N, C, mode, temp, nullptr, rows, norms, st);                      \
+        TYPE* rw = (TYPE*)rows;                                                                                             \
+        if (want_sim && want_rows) dispatch_rep_pass<true, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rw, norms, st); \
+        else if (want_sim) dispatch_rep_pass<false, TYPE>((C + 3) / 4, r, proto_scratch, hw, N, C, mode, temp, sim_out, rw, norms, st);      \
+        else launch_rep_pass<0, true, TYPE>(r, nullptr, hw, N, C, mode, temp, nullptr, rw, norms, st);                        \
     } while (0)
     if (rep_dtype == CSS_DTYPE_F32) REP_PASS_RUN(float);
     else REP_PASS_RUN(__nv_bfloat16);

@@ -34,7 +34,8 @@ __device__ __forceinline__ void flush_run(float4* part, uint32_t bits, uint32_t&
     }
 }
 
-__global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ valid_bits,
+template <typename RT>
+__global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const RT* __restrict__ rows, const uint32_t* __restrict__ valid_bits,
                                                                 int C, int N, float4* __restrict__ partials,
                                                                 uint32_t* __restrict__ touched) {
     const int t = threadIdx.x;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const float4* __
         for (int i = 0; i < 4; ++i) {
             const bool ok = p0 + i < p_end;
             b[i] = ok ? __ldg(valid_bits + p0 + i) : 0u;
-            v[i] = (ok && b[i]) ? ldg_stream4(rows + (size_t)(p0 + i) * (CSS_D / 4) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (ok && b[i]) ? row_f4(rows, (size_t)(p0 + i), t) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -130,14 +131,18 @@ __global__ void __launch_bounds__(CR_DCH * CR_SEG) class_reduce_kernel(const flo
     }
 }
 
-extern "C" int css_class_stats(const float* rows, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
+extern "C" int css_class_stats(const void* rows, int rows_dtype, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
                                float* partials, uint32_t* touched, float* class_stats, void* stream) {
     CSS_CHECK_ARG(rows && valid_bits && meta && partials && touched && class_stats, CSS_E_ARG, "css_class_stats: null pointer");
     CSS_CHECK_ARG(N > 0, CSS_E_ARG, "css_class_stats: non-positive size");
     if (int e = css_check_dims(C, D)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int G = css_class_blocks(N);
-    class_sums_kernel<<<G, CS_THREADS, 0, st>>>((const float4*)rows, valid_bits, C, N, (float4*)partials, touched);
+    CSS_CHECK_ARG(rows_dtype == CSS_DTYPE_F32 || rows_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_class_stats: rows dtype %d", rows_dtype);
+    if (rows_dtype == CSS_DTYPE_F32)
+        class_sums_kernel<float><<<G, CS_THREADS, 0, st>>>((const float*)rows, valid_bits, C, N, (float4*)partials, touched);
+    else
+        class_sums_kernel<__nv_bfloat16><<<G, CS_THREADS, 0, st>>>((const __nv_bfloat16*)rows, valid_bits, C, N, (float4*)partials, touched);
     class_reduce_kernel<<<dim3(C, CSS_D / CR_DCH), CR_DCH * CR_SEG, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
     CSS_CHECK_LAUNCH("css_class_stats", 2);
     return 0;

@@ -71,7 +71,8 @@ class _ContrastFn(torch.autograd.Function):
             rows, norms = cache.rows, cache.norms
         else:
             rows, norms = rep_rows(rep)
-        check(lib.css_class_stats(ptr(rows), ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
+        rows_dt = _lib.DTYPE_BF16 if rows.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        check(lib.css_class_stats(ptr(rows), rows_dt, ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
                                   ptr(ws.class_stats), st), "css_class_stats")
         allreduce_class_stats(ws.class_stats, mod.process_group)
         check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
@@ -89,7 +90,7 @@ class _ContrastFn(torch.autograd.Function):
         if ev is not None:                       # bench.py times the dominant kernel live, on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+        check(lib.css_score_ce(ptr(rows), rows_dt, ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
                                ptr(ws.hard_list), ptr(ws.meta), ptr(a_idx), ptr(n_idx), seed, offset, ptr(counter), N, C, D, Q, Nn,
                                float(mod.temp), ptr(ws.loss_kq), ptr(anchor_px), ptr(grad_anchor), ptr(loss), st), "css_score_ce")
         if ev is not None:

@@ -62,10 +62,10 @@ def rows_key(rep):
 
 
 def rep_rows(rep):
-    """Pixel-major copy rows [N,256] + norms [N] of an NCHW representation map (one streaming read)."""
+    """Pixel-major copy rows [N,256] (same dtype as the map) + norms [N] f32 of an NCHW representation map (one streaming read)."""
     rep, dt = _cuda_rep(rep)
     B, D, h, w = rep.shape
-    rows = torch.empty((B * h * w, D), device=rep.device, dtype=torch.float32)
+    rows = torch.empty((B * h * w, D), device=rep.device, dtype=rep.dtype)      # rows keep the map's dtype (bf16 is lossless)
     norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
@@ -85,7 +85,7 @@ def _sim(rep, prototypes, mode, temp, with_rows=False):
     scratch = _proto_scratch(rep.device)
     rows = norms = None
     if with_rows:
-        rows = torch.empty((B * h * w, D), device=rep.device, dtype=torch.float32)
+        rows = torch.empty((B * h * w, D), device=rep.device, dtype=rep.dtype)  # rows keep the map's dtype (bf16 is lossless)
         norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):

@@ -70,14 +70,15 @@ unsigned long long css_launch_count(void);
  *      pixel's D-vector against the class prototypes.  Replaces ddp_model.py:104-110 (teacher sim_mat) and
  *      :147-154 / :230-237 (student prob_all).  Needs prototypes [C,D] and proto_scratch f32[D*32] (normalised,
  *      transposed prototypes; F.normalize eps 1e-12).
- *  (b) rows f32[N*D] + norms f32[N]: the pixel-major copy (row p = pixel id p, raw values) and ||x_p||, from which the
- *      loss gathers candidate rows and accumulates class sums (loss.py:85,102,111-112,142).
+ *  (b) rows [N*D] + norms f32[N]: the pixel-major copy (row p = pixel id p, raw values, SAME dtype as rep: a bf16 map gives
+ *      lossless bf16 rows and halves the gather bytes) and ||x_p||, from which the loss gathers candidate rows and
+ *      accumulates class sums (loss.py:85,102,111-112,142).
  * NULL sim_out skips (a); NULL rows/norms skips (b).  css_sim_map is (a) alone.
  * rep_dtype: CSS_DTYPE_F32 or CSS_DTYPE_BF16 (bf16 is widened exactly; all arithmetic and all outputs stay fp32).
  */
 int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                  int B, int C, int D, int h, int w, int mode, float temp,
-                 float* sim_out, float* rows, float* norms, void* stream);
+                 float* sim_out, void* rows, float* norms, void* stream);
 int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                 int B, int C, int D, int h, int w, int mode, float temp, float* out, void* stream);
 
@@ -112,12 +113,12 @@ int css_select(const float* label, const float* mask, const float* prob, float s
 /* ---- stage 4a: per-class statistics ----------------------------------------------------------------------------------
  * Per-class feature sums and counts of this rank from the pixel-major rows: the all-reduce payload that replaces the
  * reference's all_gather (loss.py:77,81,102).  Deterministic (no atomics).
- *   rows f32[N*D] (from css_rep_pass), valid_bits u32[N], meta i32[CSS_META_WORDS] (from css_select: the local counts)
+ *   rows [N*D] of rows_dtype (from css_rep_pass), valid_bits u32[N], meta i32[CSS_META_WORDS] (from css_select: the local counts)
  *   partials  f32[css_class_blocks(N) * C * D] + touched u32[css_class_blocks(N)]   scratch
  *   class_stats f32[C*(D+1)]  row c = [sum_d ... , count]
  */
 int css_class_blocks(int N);
-int css_class_stats(const float* rows, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
+int css_class_stats(const void* rows, int rows_dtype, const uint32_t* valid_bits, const int32_t* meta, int N, int C, int D,
                     float* partials, uint32_t* touched, float* class_stats, void* stream);
 
 /* ---- stage 4b: prototype EMA --------------------------------------------------------------------------------------
@@ -151,7 +152,7 @@ int css_sample(const int32_t* meta, const float* class_cdf, uint64_t seed, uint6
  *   loss_kq f32[C*Q], anchor_px i32[C*Q] (pixel id of each anchor, -1 if none), grad_anchor f32[C*Q*D] or NULL,
  *   loss f32[1] = (1/V) sum_k (1/Q) sum_q loss_kq, exactly 0 when V <= 1.
  */
-int css_score_ce(const float* rows, const float* norms, const float* proto_hat, const float* class_cdf,
+int css_score_ce(const void* rows, int rows_dtype, const float* norms, const float* proto_hat, const float* class_cdf,
                  const int32_t* valid_list, const int32_t* hard_list, int32_t* meta,
                  const int32_t* anchor_idx, const int32_t* neg_idx, uint64_t seed, uint64_t offset, uint64_t* step_counter,
                  int N, int C, int D, int Q, int Nn, float temp,

@@ -87,12 +87,13 @@ def test_score_kernel_issues_all_row_loads_before_the_fmas():
     assert funcs, "gradient variants of score_ce_kernel not found"
     for name, body in funcs:
         ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body, flags=re.M)
+        row_load = "LDG.E.64" if "bfloat16" in name else "LDG.E.128"       # bf16 rows: 8 bytes per lane per chunk
         best = run = 0
         for op in ops:
-            if op.startswith("LDG.E.128"):
+            if op.startswith(row_load):
                 run += 1
                 best = max(best, run)
             elif op.startswith(("FFMA2", "LDS")):
                 run = 0
-        assert best >= 8, f"{name}: row loads are split by compute (longest run of LDG.E.128 = {best})"
+        assert best >= 8, f"{name}: row loads are split by compute (longest run of {row_load} = {best})"
         assert any(op.startswith("FFMA2") for op in ops), "packed fp32x2 FMAs (sm_100 FFMA2) expected in the scorer"

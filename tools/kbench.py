@@ -39,14 +39,16 @@ def main():
     ap.add_argument("--workload", default="voc321_mix")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--pool", type=int, default=4)
+    ap.add_argument("--bf16", action="store_true", help="bf16 representation maps (bf16 pixel-major rows)")
     a = ap.parse_args()
     cfg = WORKLOADS[a.workload]
     B, C, h, w, H, W, Q, Nn, temp = (cfg[k] for k in ("B", "C", "h", "w", "H", "W", "Q", "Nn", "temp"))
     host = make_inputs(cfg, 0)
     dev = torch.device("cuda")
     P = a.pool
-    rep_u = [host["rep_u"].to(dev) + 0 for _ in range(P)]
-    rep_all = [host["rep_all"].to(dev) + 0 for _ in range(P)]
+    rdt = torch.bfloat16 if a.bf16 else torch.float32
+    rep_u = [host["rep_u"].to(dev).to(rdt) + 0 for _ in range(P)]
+    rep_all = [host["rep_all"].to(dev).to(rdt) + 0 for _ in range(P)]
     pred_u = host["pred_u"].to(dev)
     label, mask = host["label"].to(dev), host["mask"].to(dev)
     protos = host["prototypes"].to(dev)
@@ -71,9 +73,10 @@ def main():
                              ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), stream_ptr()), "select")
 
     rows, norms = crit.last["rows"], crit.last["norms"]
+    rows_dt = 1 if rows.dtype == torch.bfloat16 else 0
 
     def stream(i):
-        check(lib.css_class_stats(ptr(rows), ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
+        check(lib.css_class_stats(ptr(rows), rows_dt, ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
                                   ptr(ws.class_stats), stream_ptr()), "class_stats")
 
     p2 = protos.clone()
@@ -87,7 +90,7 @@ def main():
     loss = torch.empty((), device=dev)
 
     def score(i, grad=True):
-        check(lib.css_score_ce(ptr(rows), ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
+        check(lib.css_score_ce(ptr(rows), rows_dt, ptr(norms), ptr(ws.proto_hat), ptr(ws.class_cdf), ptr(ws.valid_list),
                                ptr(ws.hard_list), ptr(ws.meta), None, None, 7, i, None, N, C, D, Q, Nn, temp, ptr(ws.loss_kq),
                                ptr(anchor_px), ptr(grad_anchor) if grad else None, ptr(loss), stream_ptr()), "score")
 
