@@ -401,3 +401,33 @@ def test_small_temperatures_online_max_path(temp):
     l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=sampler, **kw)
     np.testing.assert_allclose(loss.item(), l_or, rtol=RTOL)
     np.testing.assert_allclose(grad.cpu().numpy(), g_or, rtol=RTOL, atol=1e-6 * np.abs(g_or).max())
+
+
+@pytest.mark.parametrize("B2,C,h,w,Q,Nn", [(1, 2, 1, 3, 1, 1), (1, 32, 3, 2, 3, 5), (2, 3, 1, 1, 2, 2), (1, 4, 5, 7, 130, 1), (3, 21, 4, 4, 1, 700)])
+def test_tiny_and_ragged_shapes(B2, C, h, w, Q, Nn):
+    """Degenerate sizes: single-row maps, more classes than pixels, one query, one negative, Q not a multiple of 4,
+    Nn spanning several candidate batches.  Same checks as the large cases (selection exact, loss/grad rel 1e-4)."""
+    import css_b200
+    g = torch.Generator().manual_seed(B2 * 1000 + C * 10 + Q)
+    rep = torch.randn(B2, 256, h, w, generator=g).numpy()
+    cls = torch.randint(0, C, (B2, h, w), generator=g)
+    label = torch.nn.functional.one_hot(cls, C).permute(0, 3, 1, 2).float().numpy()
+    mask = (torch.rand(B2, 1, h, w, generator=g) < 0.9).float().numpy()
+    prob = torch.rand(B2, C, h, w, generator=g).numpy()
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.7, alpha=0.99)
+    crit = css_b200.Contrast_Loss(seed=3, **kw).cuda()
+    protos = torch.zeros(C, 256).cuda()
+    loss, grad = run_gpu(crit, rep, label, mask, prob, protos)
+    sel = crit.selection()
+    a, n = crit.sample_indices(3, 0)
+    slots = scored_slots(sel)
+    sampler = O.RecordedDraws([a.cpu().numpy()[k] for k in slots], [n.cpu().numpy()[k].reshape(-1) for k in slots])
+    p_or = np.zeros((C, 256), np.float32)
+    l_or, g_or, info = O.contrast_loss(rep, label, mask, prob, p_or, sampler=sampler, **kw)
+    check_selection(sel, info)
+    assert info["scored"] == slots
+    np.testing.assert_allclose(loss.item(), l_or, rtol=RTOL, atol=1e-7)
+    # d loss / d anchor = (S - p_hat) k - t a_hat is a difference of nearly equal vectors when hundreds of negatives are drawn
+    # from a few dozen pixels: elements far below the row's scale carry fp32 summation-order noise of ~1e-5 of that scale
+    np.testing.assert_allclose(grad.cpu().numpy(), g_or, rtol=RTOL, atol=2e-5 * max(np.abs(g_or).max(), 1e-30))
+    np.testing.assert_allclose(protos.cpu().numpy(), p_or, rtol=RTOL, atol=1e-6)
