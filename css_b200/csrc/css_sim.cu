@@ -286,8 +286,9 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
 // ---------------------------------------------------------------------------------------------------------------
 // K2: fused bilinear (align_corners=True) up-sampling + softmax + max (+ mix fusion) at crop resolution.
 // A CTA owns an 8 x 32 tile of crop pixels of one image; the few low-resolution pixels that tile touches (for 81 -> 321:
-// 4 x 10 per class) are staged ONCE in shared memory for all C classes of both maps, so the 4-tap reads are shared-memory
-// broadcasts instead of 168 L1/L2 loads per thread.  Arithmetic follows ATen's upsample_bilinear2d op for op (explicit
+// <= 5 x 11) are staged ONCE in shared memory, position-major ([pos][C rounded up to 4]) for both maps, so each of the
+// 4 taps is one 128-bit shared load per four classes instead of 168 L1/L2 loads per thread, and the interpolation runs on
+// packed fp32 pairs.  Arithmetic follows ATen's upsample_bilinear2d op for op (explicit
 // _rn intrinsics: no FMA contraction):
 //   src = ((in-1)/(out-1)) * dst ; i0 = int(src) ; i1 = i0 + (i0 < in-1) ; lam = src - i0
 //   v = (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11)
@@ -347,12 +348,69 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
     label = lab;
 }
 
+// Same result as upsample_softmax_max, for the staged tile: position-major [pos][CP] (CP = C rounded up to 4), so one
+// 128-bit shared load per tap brings four classes and the interpolation runs on packed fp32 pairs (FMUL2 / FADD2: each
+// half is the same IEEE round-to-nearest op as the scalar form, so labels stay bit-exact).  ~12 issue slots per class
+// instead of ~32 (4 LDS + 4 address LEAs + 10 scalar flops + ...): the kernel is issue-bound, not HBM-bound.
+template <int CT>
+__device__ __forceinline__ void upsample_softmax_max_tile(const float* __restrict__ tile, int C, const Taps& t, int tmode, float temp,
+                                                          float rtemp, float& conf, int& label) {
+    constexpr int CP = CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX;
+    const float4* p00 = reinterpret_cast<const float4*>(tile + t.o00 * CP);
+    const float4* p01 = reinterpret_cast<const float4*>(tile + t.o01 * CP);
+    const float4* p10 = reinterpret_cast<const float4*>(tile + t.o10 * CP);
+    const float4* p11 = reinterpret_cast<const float4*>(tile + t.o11 * CP);
+    const float2 hx = make_float2(t.hx, t.hx), lx = make_float2(t.lx, t.lx);
+    const float2 hy = make_float2(t.hy, t.hy), ly = make_float2(t.ly, t.ly);
+    const float2 rt = make_float2(rtemp, rtemp);
+    float2 v[CP / 2];
+#pragma unroll
+    for (int g = 0; g < CP / 4; ++g) {
+        const float4 a = p00[g], b = p01[g], c = p10[g], d = p11[g];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const float2 a2 = hh ? make_float2(a.z, a.w) : make_float2(a.x, a.y);
+            const float2 b2 = hh ? make_float2(b.z, b.w) : make_float2(b.x, b.y);
+            const float2 c2 = hh ? make_float2(c.z, c.w) : make_float2(c.x, c.y);
+            const float2 d2 = hh ? make_float2(d.z, d.w) : make_float2(d.x, d.y);
+            const float2 top = __fadd2_rn(__fmul2_rn(hx, a2), __fmul2_rn(lx, b2));
+            const float2 bot = __fadd2_rn(__fmul2_rn(hx, c2), __fmul2_rn(lx, d2));
+            float2 val = __fadd2_rn(__fmul2_rn(hy, top), __fmul2_rn(ly, bot));
+            if (tmode == 1) val = __fmul2_rn(val, rt);
+            else if (tmode == 2) val = make_float2(__fdiv_rn(val.x, temp), __fdiv_rn(val.y, temp));
+            v[2 * g + hh] = val;
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < CP / 2; ++i) {
+        if (CT > 0 ? (2 * i < CT) : (2 * i < C)) m = fmaxf(m, v[i].x);
+        if (CT > 0 ? (2 * i + 1 < CT) : (2 * i + 1 < C)) m = fmaxf(m, v[i].y);
+    }
+    const float2 nm = make_float2(-m, -m), l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CP / 2; ++i) {
+        const float2 x = __fmul2_rn(__fadd2_rn(v[i], nm), l2e);   // (v - m) * log2(e), as the scalar form
+        if (CT > 0 ? (2 * i < CT) : (2 * i < C)) sum += (v[i].x = ex2_approx(x.x));
+        if (CT > 0 ? (2 * i + 1 < CT) : (2 * i + 1 < C)) sum += (v[i].y = ex2_approx(x.y));
+    }
+    int lab = 0;
+#pragma unroll
+    for (int cc = CP - 1; cc >= 0; --cc) {
+        const float e = (cc & 1) ? v[cc >> 1].y : v[cc >> 1].x;
+        if ((CT > 0 ? (cc < CT) : (cc < C)) && e == 1.f) lab = cc;
+    }
+    conf = __fdiv_rn(1.f, sum);
+    label = lab;
+}
+
 template <bool STAGED, int CT>
-__global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
+__global__ void __launch_bounds__(K2_TH * K2_TW, STAGED ? 5 : 1) upsample_label_fuse_kernel(
     const float* __restrict__ sim, const float* __restrict__ logits, float temp, float rtemp, int tmode, int fuse_mode, int C, int h, int w, int H, int W,
     float ry, float rx, int tile_cap, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
     int64_t* __restrict__ label_cls, float* __restrict__ fused) {
-    extern __shared__ float tile[];                 // [2 maps][C][in_th * in_tw]  (STAGED only)
+    extern __shared__ __align__(16) float tile[];   // [2 maps][tile_cap positions][CP classes]  (STAGED only)
     const int b = blockIdx.z;
     const int Y0 = blockIdx.y * K2_TH, X0 = blockIdx.x * K2_TW;
     const int Y = Y0 + (threadIdx.x >> 5), X = X0 + (threadIdx.x & 31);
@@ -366,13 +424,25 @@ __global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
         const int in_th = min(ye + 1, h - 1) - ys0 + 1;
         in_tw = min(xe + 1, w - 1) - xs0 + 1;
         cstride = in_th * in_tw;                    // <= tile_cap by construction of the launch
-        const int n = C * cstride;
-        for (int i = threadIdx.x; i < n; i += K2_TH * K2_TW) {
-            const int c = i / cstride, r = i - c * cstride;
-            const int yy = r / in_tw, xx = r - yy * in_tw;
-            const size_t g = ((size_t)b * C + c) * hw + (size_t)(ys0 + yy) * w + xs0 + xx;
-            if (sim) tile[c * cstride + r] = __ldg(sim + g);
-            if (logits) tile[C * tile_cap + c * cstride + r] = __ldg(logits + g);
+        // transpose NCHW -> [pos][CP] through a 4-position x 8-class lane pattern: the global side reads 16-byte runs,
+        // the shared side lands in 32 distinct banks for CP = 24 (stride 24 floats: rows 0,24,16,8 + 8 classes each)
+        constexpr int CP = CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX;
+        // a warp walks 4-position x 8-class blocks; the only run-time division, r -> (yy, xx), is done in fp32 (exact: r < 2^12)
+        constexpr int CB = (CP + 7) >> 3;
+        const int RB = (cstride + 3) >> 2;
+        const float inv_tw = __frcp_ru((float)in_tw);
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int blk = wid; blk < RB * CB; blk += K2_TH) {
+            const int c_hi = blk % CB, r_hi = blk / CB;              // CB is a compile-time constant
+            const int r = r_hi * 4 + (lane & 3), c = c_hi * 8 + (lane >> 2);
+            if (r < cstride && c < CP) {
+                int yy = (int)(((float)r + 0.5f) * inv_tw);
+                yy -= (yy * in_tw > r);
+                const int xx = r - yy * in_tw;
+                const size_t g = ((size_t)b * C + c) * hw + (size_t)(ys0 + yy) * w + xs0 + xx;
+                if (sim) tile[r * CP + c] = c < C ? __ldg(sim + g) : 0.f;
+                if (logits) tile[(tile_cap + r) * CP + c] = c < C ? __ldg(logits + g) : 0.f;
+            }
         }
         __syncthreads();
     }
@@ -395,14 +465,14 @@ __global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
     int lr = -1, lc = -2;
     if (sim) {
         float cf;
-        if (STAGED) upsample_softmax_max<CT>(tile, C, cstride, t, tmode, temp, rtemp, cf, lr);
+        if (STAGED) upsample_softmax_max_tile<CT>(tile, C, t, tmode, temp, rtemp, cf, lr);
         else upsample_softmax_max<CT>(sim + (size_t)b * C * hw, C, hw, t, tmode, temp, rtemp, cf, lr);
         if (conf_rep) conf_rep[o] = cf;
         if (label_rep) label_rep[o] = lr;
     }
     if (logits) {
         float cf;
-        if (STAGED) upsample_softmax_max<CT>(tile + C * tile_cap, C, cstride, t, 0, 1.f, 1.f, cf, lc);
+        if (STAGED) upsample_softmax_max_tile<CT>(tile + (size_t)tile_cap * (CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX), C, t, 0, 1.f, 1.f, cf, lc);
         else upsample_softmax_max<CT>(logits + (size_t)b * C * hw, C, hw, t, 0, 1.f, 1.f, cf, lc);
         if (conf_cls) conf_cls[o] = cf;
         if (label_cls) label_cls[o] = lc;
@@ -429,7 +499,8 @@ extern "C" int css_upsample_label_fuse(const float* sim, const float* logits, fl
     const int in_th = (int)fminf((float)h, ceilf(ry * (K2_TH - 1)) + 3.f);
     const int in_tw = (int)fminf((float)w, ceilf(rx * (K2_TW - 1)) + 3.f);
     const int tile_cap = in_th * in_tw;
-    const size_t smem = (size_t)2 * C * tile_cap * sizeof(float);
+    const int cp = (C == 21 || C == 19) ? ((C + 3) & ~3) : CSS_CMAX;       // class pitch of the staged tile (see the kernel)
+    const size_t smem = (size_t)2 * cp * tile_cap * sizeof(float);
     dim3 grid((W + K2_TW - 1) / K2_TW, (H + K2_TH - 1) / K2_TH, B);
     cudaStream_t st = (cudaStream_t)stream;
     // x / temp == x * (1/temp) exactly when temp is a power of two (the shipped 0.5 / 0.25); otherwise divide like the reference
