@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(HERE, "libcss_b200.so")
 DTYPE_F32, DTYPE_BF16 = 0, 1
 SIM_COS, SIM_SOFTMAX = 0, 1
 FUSE_NONE, FUSE_MIX = 0, 1
+LABEL_F32, LABEL_I64 = 0, 1
+CUT_CUTOUT, CUT_CUTMIX, CUT_CLASSMIX = 0, 1, 2
 META_WORDS = 256
 META_V, META_N_VALID, META_N_HARD, META_CLS_OF_SLOT, META_SLOT_OF_CLS = 0, 32, 64, 96, 128
 CMAX = 32
@@ -40,6 +42,9 @@ SIGNATURES = {
     "css_atl_blocks": (c_int, [c_int, c_int]),
     "css_atl_forward": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "css_atl_backward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
+    "css_aug_index": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
+    "css_aug_maps": (c_int, [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "css_cut_mix": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "css_threshold_glue": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
 }
 

@@ -11,7 +11,9 @@ import sys
 import types
 
 
-def install(reference_root=None, stub_shutup=True):
+def install(reference_root=None, stub_shutup=True, gpu_aug=False):
+    """gpu_aug=True also routes the shells' augmentation calls through css_b200.aug: the label / confidence maps stay on the
+    GPU (same outputs, same RNG consumption as dataset_helpers/VOC.py:312-477); the default keeps the reference's functions."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     if stub_shutup and "shutup" not in sys.modules:
@@ -31,6 +33,11 @@ def install(reference_root=None, stub_shutup=True):
                  "generate_cut_gather_2", "generate_cut_gather_3"):
         # resolved through the reference module at call time, exactly like ddp_model.py:6,121,127,132 does
         setattr(h, name, (lambda n: (lambda *a, **k: getattr(ref_model, n)(*a, **k)))(name))
+    if gpu_aug:
+        from . import aug as _aug
+        for name in ("batch_transform", "batch_transform_2", "batch_transform_3", "generate_cut_gather",
+                     "generate_cut_gather_2", "generate_cut_gather_3"):
+            setattr(h, name, getattr(_aug, name))
     ref_loss.Contrast_Loss = _loss.Contrast_Loss
     ref_loss.Attention_Threshold_Loss = _loss.Attention_Threshold_Loss
     ref_model.Model_ori_pseudo = _models.Model_ori_pseudo

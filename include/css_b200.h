@@ -187,6 +187,40 @@ int css_atl_forward(const float* pred, const int64_t* label, const float* conf, 
 int css_atl_backward(const float* grad_out, const float* pred, const int64_t* label, const float* lse, const float* scale,
                      int B, int C, int H, int W, float* grad_pred, void* stream);
 
+/* ---- augmentation hand-off of the label / confidence maps ------------------------------------------------
+ * The maps' trip tensor -> PIL 'L' image -> NEAREST resize -> bottom/right pad (255 / 0) -> crop -> hflip -> tensor, kept on the
+ * GPU.  Replaces, for the maps, tensor_to_pil_* + transform_* + the host->device copies of batch_transform_*
+ * (dataset_helpers/VOC.py:64-352); the image keeps the PIL path, which is where the host draws `geometry`.
+ *   geometry i32[B,5] (device) = resized_h, resized_w, top, left, flip per image
+ *   css_aug_index: ymap / xmap i32[B,max_r] = Pillow's NEAREST source index tables for H -> resized_h, W -> resized_w
+ *                  (running double sum, replayed sequentially), max_r >= every resized_h / resized_w
+ *   css_aug_maps : label_a/label_b [B,H,W] f32 or i64 (label_dtype; values 0..254, 255 or -1 = ignore), conf_a/conf_b [B,H,W] f32,
+ *                  any of them nullable -> out_label_* i64[B,ch,cw] (-1 = ignore), out_conf_* f32 = floor(conf * 255) / 255
+ */
+#define CSS_LABEL_F32 0
+#define CSS_LABEL_I64 1
+int css_aug_index(const int32_t* geometry, int B, int H, int W, int max_r, int32_t* ymap, int32_t* xmap, void* stream);
+int css_aug_maps(const void* label_a, const void* label_b, int label_dtype, const float* conf_a, const float* conf_b,
+                 const int32_t* geometry, const int32_t* ymap, const int32_t* xmap, int B, int H, int W, int max_r,
+                 int ch, int cw, int64_t* out_label_a, int64_t* out_label_b, float* out_conf_a, float* out_conf_b,
+                 void* stream);
+
+/* CutOut / CutMix / ClassMix of one rank's batch in one launch.  Replaces the per-image loop of generate_cut_gather_*
+ * (dataset_helpers/VOC.py:354-477): out[i] = keep ? own[i] : partner[(i + 1) % B]; CutOut writes 0 (image, conf) / -1 (label_a)
+ * instead of the partner.  keep = pixel outside boxes[i] = (y0, y1, x0, x1)  (cutout, cutmix), or own label_a value v in
+ * class_sets[i] (bit v + 1, v in [-1, 62])  (classmix).  The p_* maps are the batch the partners come from: the same
+ * pointers on one rank, rank 0's batch otherwise (the reference's partner index always lands in rank 0's slice).
+ *   image [B,CH,H,W] f32, label_a (label_b nullable) [B,H,W] i64, conf_a (conf_b nullable) [B,H,W] f32
+ */
+#define CSS_CUT_CUTOUT 0
+#define CSS_CUT_CUTMIX 1
+#define CSS_CUT_CLASSMIX 2
+int css_cut_mix(const float* image, const int64_t* label_a, const int64_t* label_b, const float* conf_a, const float* conf_b,
+                const float* p_image, const int64_t* p_label_a, const int64_t* p_label_b, const float* p_conf_a,
+                const float* p_conf_b, const int32_t* boxes, const uint64_t* class_sets, int mode, int B, int CH, int H, int W,
+                float* out_image, int64_t* out_label_a, int64_t* out_label_b, float* out_conf_a, float* out_conf_b,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,3 +390,102 @@ def attention_threshold_loss(pred, pseudo_label, logits, strong_threshold, want_
         coef = np.where(sel, (weighting[:, None, None] / n).astype(f32), f32(0))
         grad = ((soft - onehot) * coef[:, None]).astype(f32)
     return f32(out), grad
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the label / confidence maps' trip through the augmentation (tensor -> PIL 'L' image -> nearest
+# resize -> pad -> crop -> flip -> tensor), restated as index arithmetic.  dataset_helpers/VOC.py:126-196 (transform_2;
+# transform :64-124 and transform_3 :198-274 are the same with other map counts), :284-302 (tensor_to_pil_*).
+# The arithmetic is Pillow's (NEAREST resize = ImagingScaleAffine, Pillow 9.1 .. 12.x) and torchvision's
+# (to_pil_image: mul(255).byte(); to_tensor: byte / 255), neither vendored in the reference; pinned by
+# tests/golden/aug_*.npz, generated by running the reference's own batch_transform_* here.
+# ---------------------------------------------------------------------------------------------------------------
+def pil_nearest_table(n_in, n_out):
+    """Source index of every output pixel of Image.resize((.., n_out), NEAREST) along one axis.
+    Pillow walks `pos = 0.5 * a; pos += a` in double with a = n_in / n_out and truncates (Geometry.c, affine scale path),
+    so the table is a running sum, not (x + 0.5) * a."""
+    a = np.float64(n_in) / np.float64(n_out)
+    pos = np.float64(0.0) + a * np.float64(0.5)
+    out = np.empty(n_out, np.int64)
+    for x in range(n_out):
+        out[x] = int(pos)
+        pos = pos + a
+    return np.minimum(out, n_in - 1)
+
+
+def label_to_byte(label):
+    """tensor_to_pil_*: (label.float() / 255) -> to_pil_image -> mul(255).byte().  Identity on 0..255, -1 wraps to 255."""
+    f = (np.asarray(label).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    return (f * np.float32(255.0)).astype(np.float32).astype(np.int64).astype(np.uint8)
+
+
+def conf_to_byte(conf):
+    """to_pil_image of a float map: mul(255).byte() (truncation): the 8-bit quantisation of the confidences."""
+    return (np.asarray(conf, np.float32) * np.float32(255.0)).astype(np.float32).astype(np.int64).astype(np.uint8)
+
+
+def byte_to_label(b):
+    """(to_tensor(label) * 255).long(), 255 -> -1  (VOC.py:184-185)."""
+    v = ((b.astype(np.float32) / np.float32(255.0)).astype(np.float32) * np.float32(255.0)).astype(np.float32).astype(np.int64)
+    v[v == 255] = -1
+    return v
+
+
+def byte_to_conf(b):
+    return (b.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def aug_maps(labels, confs, geometry, crop_hw):
+    """labels / confs: lists of [B,H,W] maps.  geometry: int array [B,5] = (resized_h, resized_w, top, left, flip) per
+    image, i.e. what transform_* drew.  Returns (labels int64 with -1 = ignore, confs float32 multiples of 1/255)."""
+    ch, cw = crop_hw
+    B, H, W = np.asarray((labels + confs)[0]).shape
+    out_l = [np.empty((B, ch, cw), np.int64) for _ in labels]
+    out_c = [np.empty((B, ch, cw), np.float32) for _ in confs]
+    for b in range(B):
+        rh, rw, top, left, flip = (int(v) for v in geometry[b])
+        ymap, xmap = pil_nearest_table(H, rh), pil_nearest_table(W, rw)
+        ph, pw = max(rh, ch), max(rw, cw)                         # bottom / right constant padding (VOC.py:143-151)
+        for maps, outs, to_byte, from_byte, fill in ((labels, out_l, label_to_byte, byte_to_label, 255),
+                                                    (confs, out_c, conf_to_byte, byte_to_conf, 0)):
+            for m, o in zip(maps, outs):
+                img = np.full((ph, pw), fill, np.uint8)
+                img[:rh, :rw] = to_byte(np.asarray(m[b]))[ymap][:, xmap]
+                img = img[top:top + ch, left:left + cw]
+                if flip:
+                    img = img[:, ::-1]
+                o[b] = from_byte(img)
+    return out_l, out_c
+
+
+def cut_mix(image, labels, confs, mode, boxes=None, class_sets=None, partner=None):
+    """generate_cut_gather_* on one rank's slice (VOC.py:354-477).  boxes [B,4] = (y0, y1, x0, x1) of the region whose
+    mask is 0; class_sets: per image, the label values whose pixels KEEP the own image (classmix).  partner =
+    (image, labels, confs) of the batch the (i+1) % B partner is taken from (rank 0's; the own batch when None)."""
+    B, _, H, W = image.shape
+    p_img, p_lab, p_conf = partner if partner is not None else (image, labels, confs)
+    o_img = np.empty_like(image)
+    o_lab = [np.empty((B, H, W), np.int64) for _ in labels]
+    o_conf = [np.empty((B, H, W), np.float32) for _ in confs]
+    for i in range(B):
+        if mode == "classmix":
+            keep = np.isin(labels[0][i], np.asarray(class_sets[i]))
+        else:
+            keep = np.ones((H, W), bool)
+            y0, y1, x0, x1 = (int(v) for v in boxes[i])
+            keep[y0:y1, x0:x1] = False
+        if mode == "cutout":
+            o_img[i] = np.where(keep, image[i], 0)
+            o_lab[0][i] = np.where(keep, labels[0][i], -1)
+            for k in range(1, len(labels)):
+                o_lab[k][i] = labels[k][i]
+            for k in range(len(confs)):
+                o_conf[k][i] = np.where(keep, confs[k][i], 0)
+            continue
+        j = (i + 1) % B
+        o_img[i] = np.where(keep, image[i], p_img[j])
+        for k in range(len(labels)):
+            o_lab[k][i] = np.where(keep, labels[k][i], p_lab[k][j])
+        for k in range(len(confs)):
+            o_conf[k][i] = np.where(keep, confs[k][i], p_conf[k][j])
+    return o_img, o_lab, o_conf

@@ -176,6 +176,105 @@ def atl_case(name, *, B, C, H, W, thr, seed):
     print(f"  {name}: loss={loss.item():.6f}")
 
 
+def _seed_all(seed):
+    import random
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def _aug_inputs(B, C, H, W, seed, int_labels):
+    import torchvision.transforms.functional as TF
+    g = synth._gen(seed)
+    image = TF.normalize(torch.rand(B, 3, H, W, generator=g), mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    cls = synth.class_map(B, C, H, W, g, ignore_frac=0.1, block=5)          # -1 = ignore
+    cls2 = synth.class_map(B, C, H, W, g, ignore_frac=0.1, block=7)
+    if not int_labels:                                                        # the fused float map of Model_mix: 255 = ignore
+        cls = torch.where(cls < 0, torch.full_like(cls, 255), cls).float()
+        cls2 = torch.where(cls2 < 0, torch.full_like(cls2, 255), cls2).float()
+    return image, cls, cls2, torch.rand(B, H, W, generator=g), torch.rand(B, H, W, generator=g)
+
+
+def aug_case(name, *, maps, B, C, H, W, crop, scale, augmentation, seed, int_labels=False):
+    """batch_transform / _2 / _3 of the reference (dataset_helpers/VOC.py:312-352) under fixed Python / NumPy / torch seeds.
+    The bundle also stores the geometry css_b200.aug draws from the same seeds (checked here against the reference's
+    outputs through the oracle), so the GPU-side replay can be tested without PIL."""
+    load_reference()
+    import generalframeworks.dataset_helpers.VOC as V
+    import torchvision.transforms.functional as TF
+    from css_b200 import aug
+    from oracle import css_oracle as O
+    image, l1, l2, c1, c2 = _aug_inputs(B, C, H, W, seed, int_labels)
+    _seed_all(seed)
+    if maps == 1:
+        r = V.batch_transform(image, l1, c1, crop_size=crop, scale_size=scale, augmentation=augmentation)
+        labels, confs, ref_l, ref_c = [l1], [c1], [r[1]], [r[2]]
+    elif maps == 2:
+        r = V.batch_transform_2(image, l1, c1, c2, crop_size=crop, scale_size=scale, augmentation=augmentation)
+        labels, confs, ref_l, ref_c = [l1], [c1, c2], [r[1]], [r[2], r[3]]
+    else:
+        r = V.batch_transform_3(image, l1, l2, c1, c2, crop_size=crop, scale_size=scale, augmentation=augmentation)
+        labels, confs, ref_l, ref_c = [l1, l2], [c1, c2], [r[1], r[2]], [r[3], r[4]]
+    _seed_all(seed)
+    host = aug._unnormalise(image)
+    mine = [aug._augment_image(TF.to_pil_image(host[k]), crop, scale, augmentation) for k in range(B)]
+    geometry = np.asarray([m[1] for m in mine], np.int32)
+    assert torch.equal(torch.stack([m[0] for m in mine]), r[0]), "image path / RNG order drifted from the reference"
+    ol, oc = O.aug_maps([_np(t) for t in labels], [_np(t) for t in confs], geometry, crop)
+    assert all(np.array_equal(a, _np(b)) for a, b in zip(ol, ref_l)) and all(np.array_equal(a, _np(b)) for a, b in zip(oc, ref_c))
+    d = dict(maps=maps, seed=seed, crop=np.asarray(crop), scale=np.asarray(scale, np.float64), augmentation=augmentation,
+             image=_np(image), geometry=geometry, out_image=_np(r[0]))
+    for i, t in enumerate(labels):
+        d[f"label{i}"] = _np(t)
+        d[f"out_label{i}"] = _np(ref_l[i]).astype(np.int16)
+    for i, t in enumerate(confs):
+        d[f"conf{i}"] = _np(t)
+        d[f"out_conf{i}"] = _np(ref_c[i])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"  {name}: geometry {geometry.tolist()}")
+
+
+def cut_case(name, *, maps, mode, B, C, H, W, seed):
+    """generate_cut_gather / _2 / _3 of the reference (VOC.py:354-477) on a single-process group."""
+    load_reference()
+    import generalframeworks.dataset_helpers.VOC as V
+    from css_b200 import aug
+    from oracle import css_oracle as O
+    image, l1, l2, c1, c2 = _aug_inputs(B, C, H, W, seed, True)
+    _seed_all(seed)
+    if maps == 1:
+        r = V.generate_cut_gather(image.clone(), l1.clone(), c1.clone(), mode=mode)
+        labels, confs, ref_l, ref_c = [l1], [c1], [r[1]], [r[2]]
+    elif maps == 2:
+        r = V.generate_cut_gather_2(image.clone(), l1.clone(), c1.clone(), c2.clone(), mode=mode)
+        labels, confs, ref_l, ref_c = [l1], [c1, c2], [r[1]], [r[2], r[3]]
+    else:
+        r = V.generate_cut_gather_3(image.clone(), l1.clone(), l2.clone(), c1.clone(), c2.clone(), mode=mode)
+        labels, confs, ref_l, ref_c = [l1, l2], [c1, c2], [r[1], r[2]], [r[3], r[4]]
+    _seed_all(seed)
+    boxes = np.zeros((B, 4), np.int32)
+    sets = np.full((B, 64), -100, np.int32)                                  # ragged class sets, padded with -100
+    if mode == "classmix":
+        for i in range(B):
+            chosen = aug.draw_class_set(labels[0][i])
+            sets[i, :len(chosen)] = chosen
+    else:
+        boxes = np.asarray([aug.draw_cut_box(H, W, 2) for _ in range(B)], np.int32)
+    o_img, o_lab, o_conf = O.cut_mix(_np(image), [_np(t) for t in labels], [_np(t) for t in confs], mode, boxes=boxes,
+                                     class_sets=[[v for v in row if v != -100] for row in sets])
+    assert np.array_equal(o_img, _np(r[0])), "cut_mix restatement drifted from the reference"
+    assert all(np.array_equal(a, _np(b)) for a, b in zip(o_lab, ref_l)) and all(np.array_equal(a, _np(b)) for a, b in zip(o_conf, ref_c))
+    d = dict(maps=maps, mode=mode, seed=seed, image=_np(image), boxes=boxes, class_sets=sets, out_image=_np(r[0]))
+    for i, t in enumerate(labels):
+        d[f"label{i}"] = _np(t).astype(np.int16)
+        d[f"out_label{i}"] = _np(ref_l[i]).astype(np.int16)
+    for i, t in enumerate(confs):
+        d[f"conf{i}"] = _np(t)
+        d[f"out_conf{i}"] = _np(ref_c[i])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"  {name}: boxes {boxes.tolist()}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     D = 256
@@ -220,6 +319,17 @@ def main():
     glue_case("glue_mix", strategy="mix", B=2, C=21, H=33, W=33, h=9, w=9, weak=0.7, seed=81)
     glue_case("glue_cross", strategy="cross", B=2, C=19, H=25, W=37, h=7, w=10, weak=0.7, seed=83)
     glue_case("glue_ori", strategy="ori", B=1, C=21, H=40, W=40, h=10, w=10, weak=0.7, seed=87)
+
+    print("augmentation hand-off cases")
+    aug_case("aug_t2_scale", maps=2, B=3, C=21, H=41, W=47, crop=(32, 36), scale=(0.5, 1.5), augmentation=False, seed=7)
+    aug_case("aug_t2_flip", maps=2, B=3, C=21, H=41, W=47, crop=(41, 47), scale=(1.0, 1.0), augmentation=True, seed=7,
+             int_labels=True)
+    aug_case("aug_t3_city", maps=3, B=3, C=19, H=45, W=52, crop=(50, 40), scale=(0.5, 2.0), augmentation=True, seed=9)
+    aug_case("aug_t1_ori", maps=1, B=2, C=21, H=33, W=33, crop=(33, 33), scale=(0.5, 1.5), augmentation=True, seed=13)
+    cut_case("cut_cutmix_2", maps=2, mode="cutmix", B=3, C=21, H=33, W=37, seed=21)
+    cut_case("cut_cutmix_3", maps=3, mode="cutmix", B=2, C=19, H=30, W=30, seed=22)
+    cut_case("cut_cutout_1", maps=1, mode="cutout", B=3, C=21, H=33, W=37, seed=23)
+    cut_case("cut_classmix_2", maps=2, mode="classmix", B=3, C=21, H=33, W=37, seed=24)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,12 @@ def test_install_patches_reference_modules():
             assert torch.allclose(e, s)
         m.ema_update()                      # step 1: decay = 0.5
         assert m.step == 2 and len(before) > 0
+        # gpu_aug=True points the augmentation hooks at css_b200.aug (maps stay on the GPU), the default at the reference
+        from css_b200 import aug
+        assert models.hooks.batch_transform_2 is not aug.batch_transform_2
+        install.install(reference_root=REF, gpu_aug=True)
+        assert models.hooks.batch_transform_2 is aug.batch_transform_2
+        assert models.hooks.generate_cut_gather_3 is aug.generate_cut_gather_3
     finally:
         for k, v in saved_hooks.items():
             setattr(models.hooks, k, v)

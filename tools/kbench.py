@@ -114,6 +114,29 @@ def main():
         (gr,) = torch.autograd.grad(atl(pp_, lu, cu), pp_)
 
     res["attention_threshold_loss fwd+bwd (8(f)-3, not in path sum)"] = timeit(atl_step, a.iters)
+    # 8(f)-2: both trips of the maps through the augmentation + CutMix, at the crop size
+    from css_b200 import aug
+    import numpy as np
+    rng = np.random.default_rng(0)
+    geo = np.zeros((B, 5), np.int32)
+    for b in range(B):
+        r = rng.uniform(0.5, 1.5)
+        rh, rw = int(H * r), int(W * r)
+        geo[b] = (rh, rw, rng.integers(0, max(rh, H) - H + 1), rng.integers(0, max(rw, W) - W + 1), b & 1)
+    geo_d = torch.from_numpy(geo).to(dev)
+    fused = torch.where(lu < 0, torch.full_like(lu, 255), lu).float()
+    cu2 = torch.rand(B, H, W, generator=g0).to(dev)
+    res["aug maps trip: index + 3 maps (8(f)-2, not in path sum)"] = timeit(
+        lambda i: aug.transform_maps([fused], [cu, cu2], geo_d, (H, W), max_resized=int(1.5 * max(H, W)) + 1), a.iters)
+    img = torch.randn(B, 3, H, W, generator=g0).to(dev)
+    boxes = torch.tensor([[H // 4, 3 * H // 4, W // 8, 7 * W // 8]] * B, dtype=torch.int32, device=dev)
+    o_img, o_l, o_c, o_c2 = torch.empty_like(img), torch.empty_like(lu), torch.empty_like(cu), torch.empty_like(cu)
+
+    def cutmix(i):
+        check(lib.css_cut_mix(ptr(img), ptr(lu), None, ptr(cu), ptr(cu2), ptr(img), ptr(lu), None, ptr(cu), ptr(cu2), ptr(boxes), None,
+                              _lib.CUT_CUTMIX, B, 3, H, W, ptr(o_img), ptr(o_l), None, ptr(o_c), ptr(o_c2), stream_ptr()), "cut_mix")
+
+    res["cut_mix image + 3 maps (8(f)-2, not in path sum)"] = timeit(cutmix, a.iters)
     res["select (3 kernels)"] = timeit(select, a.iters)
     res["class_stats (+reduce)"] = timeit(stream, a.iters)
     res["rep_rows only (ori flow)"] = timeit(lambda i: css_b200.ops.rep_rows(rep_all[i % P]), a.iters)
@@ -121,8 +144,7 @@ def main():
     res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
     res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
     res["grad_scatter (+memset)"] = timeit(scatter, a.iters)
-    tot = sum(v for k, v in res.items() if k not in ("score_ce fwd only", "rep_rows only (ori flow)", "threshold_glue K0 (8(f)-1, not in path sum)",
-                                            "attention_threshold_loss fwd+bwd (8(f)-3, not in path sum)"))
+    tot = sum(v for k, v in res.items() if "not in path sum" not in k and k not in ("score_ce fwd only", "rep_rows only (ori flow)"))
     for k, v in res.items():
         print(f"{k:60s} {v:9.1f} us")
     print(f"{'sum (path)':34s} {tot:9.1f} us")
