@@ -145,3 +145,52 @@ def test_cut_mix_full_size_vs_oracle_with_partner_batch():
         np.testing.assert_array_equal(o[0].cpu().numpy(), r[0])
         for a, b in zip(o[1] + o[2], r[1] + r[2]):
             np.testing.assert_array_equal(a.cpu().numpy(), b)
+
+
+def test_model_mix_shell_with_gpu_aug_hooks():
+    """Model_mix wired to css_b200.aug (install(gpu_aug=True) does this): the shell's output equals the three augmentation
+    calls of ddp_model.py:121-135 made by hand on the stage-1/2 outputs under the same seeds, with the reference's dtypes."""
+    import css_b200
+    from css_b200 import aug, models
+
+    class Stub(torch.nn.Module):
+        def __init__(self, outs):
+            super().__init__()
+            self.outs, self.i = outs, 0
+
+        def forward(self, x):
+            o = self.outs[self.i % len(self.outs)]
+            self.i += 1
+            return o
+
+    g = load_golden("stage12_mix_c21")
+    B, C, H, W, temp = int(g["B"]), int(g["C"]), int(g["H"]), int(g["W"]), float(g["temp"])
+    saved = dict(vars(models.hooks))
+    try:
+        models.hooks.network_factory = lambda enc, **kw: torch.nn.Conv2d(1, 1, 1)
+        for n in ("batch_transform", "batch_transform_2", "batch_transform_3", "generate_cut_gather", "generate_cut_gather_2",
+                  "generate_cut_gather_3"):
+            setattr(models.hooks, n, getattr(aug, n))
+        cfg = {"Dataset": {"crop_size": (H, W), "scale_size": (0.5, 1.5), "mix_mode": "cutmix"}}
+        m = models.Model_mix(None, num_classes=C, output_dim=256, config=cfg, temp=temp).cuda()
+        rep_all, pred_all = dev(g["rep_all"]), dev(g["pred_all"])
+        m.ema_model = Stub([(dev(g["pred_u"]), dev(g["rep_u"]))])
+        m.model = Stub([(pred_all[:B], rep_all[:B]), (pred_all[B:], rep_all[B:])])
+        img = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1)).cuda()
+        protos = dev(g["prototypes"])
+        seed_all(77)
+        r = m(img, img, protos)
+        seed_all(77)
+        o = css_b200.ops.pseudo_labels(dev(g["rep_u"]), dev(g["pred_u"]), protos, temp, (H, W), fuse="mix")
+        a = aug.batch_transform_2(img, o["fused"], o["conf_cls"], o["conf_rep"], crop_size=(H, W), scale_size=(0.5, 1.5), augmentation=False)
+        a = aug.generate_cut_gather_2(*a, mode="cutmix")
+        a = aug.batch_transform_2(*a, crop_size=(H, W), scale_size=(1.0, 1.0), augmentation=True)
+        assert r[2].dtype == torch.int64 and r[3].dtype == torch.float32 and r[2].shape == (B, H, W)
+        assert torch.equal(r[2], a[1]) and torch.equal(r[3], a[2]) and torch.equal(r[4], a[3])
+        lab = r[2].cpu().numpy()
+        assert lab.min() >= -1 and lab.max() < C
+        q = r[3].cpu().numpy() * np.float32(255)
+        np.testing.assert_allclose(q, np.round(q), atol=1e-4)         # confidences come back as multiples of 1/255
+    finally:
+        for k, v in saved.items():
+            setattr(models.hooks, k, v)
