@@ -535,46 +535,3 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
     CSS_CHECK_LAUNCH("css_score_ce", 3);
     return 0;
 }
-
-// -------------------------------------------------------------------------------------------------------------------
-// backward: grad_rep = 0 ; grad_rep[b, :, y, x] += grad_out * grad_anchor[kq, :] at every anchor pixel.
-// Autograd needs the dense [B2, 256, h, w] tensor, so the compulsory traffic is one streaming write of it: a linear
-// memset (the only pattern that writes this NCHW buffer at HBM speed: single-pass variants that fold the anchor rows into
-// a per-plane or flat sweep were measured 2x slower) followed by <= V*Q*256 red.global.add.f32.
-// -------------------------------------------------------------------------------------------------------------------
-#define GS_PER_BLOCK 8
-// each CTA handles GS_PER_BLOCK anchors: all pixel ids and gradient rows are loaded first (independent loads), then the
-// reductions are issued; thread d owns channel d (stride h*w in the NCHW gradient)
-__global__ void __launch_bounds__(CSS_D) grad_scatter_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
-                                                             const float* __restrict__ grad_anchor, int n_anchor, int hw,
-                                                             float* __restrict__ grad_rep) {
-    const int base = blockIdx.x * GS_PER_BLOCK;
-    int px[GS_PER_BLOCK];
-    float g[GS_PER_BLOCK];
-#pragma unroll
-    for (int i = 0; i < GS_PER_BLOCK; ++i) px[i] = (base + i < n_anchor) ? __ldg(anchor_px + base + i) : -1;
-    const float go = __ldg(grad_out);
-#pragma unroll
-    for (int i = 0; i < GS_PER_BLOCK; ++i)
-        g[i] = (px[i] >= 0) ? ldg_stream(grad_anchor + (size_t)(base + i) * CSS_D + threadIdx.x) : 0.f;
-#pragma unroll
-    for (int i = 0; i < GS_PER_BLOCK; ++i) {
-        if (px[i] < 0) continue;
-        const int b = px[i] / hw, s = px[i] - b * hw;
-        atomicAdd(grad_rep + ((size_t)b * CSS_D + threadIdx.x) * hw + s, go * g[i]);
-    }
-}
-
-extern "C" int css_grad_scatter(const float* grad_out, const int32_t* anchor_px, const float* grad_anchor, int n_anchor, int B2,
-                                int D, int h, int w, float* grad_rep, void* stream) {
-    CSS_CHECK_ARG(grad_out && anchor_px && grad_anchor && grad_rep, CSS_E_ARG, "css_grad_scatter: null pointer");
-    CSS_CHECK_ARG(n_anchor > 0 && B2 > 0 && h > 0 && w > 0, CSS_E_ARG, "css_grad_scatter: non-positive size");
-    CSS_CHECK_ARG(D == CSS_D, CSS_E_DIM, "css_grad_scatter: D must be %d", CSS_D);
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(grad_rep, 0, sizeof(float) * (size_t)B2 * D * h * w, st);
-    if (e != cudaSuccess) { css_set_error("css_grad_scatter: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    grad_scatter_kernel<<<(n_anchor + GS_PER_BLOCK - 1) / GS_PER_BLOCK, CSS_D, 0, st>>>(grad_out, anchor_px, grad_anchor, n_anchor, h * w,
-                                                                                      grad_rep);
-    CSS_CHECK_LAUNCH("css_grad_scatter", 1);
-    return 0;
-}

@@ -54,7 +54,10 @@ def test_stage12_against_reference_golden(name):
 
 @pytest.mark.parametrize("B,C,h,w,H,W,temp", [(2, 21, 81, 81, 321, 321, 0.5), (1, 19, 49, 97, 193, 385, 0.5),
                                                (2, 21, 17, 23, 50, 70, 0.1), (1, 3, 5, 4, 5, 4, 0.25),
-                                               (1, 32, 6, 6, 1, 1, 0.5)])
+                                               (1, 32, 6, 6, 1, 1, 0.5),
+                                               (1, 21, 30, 30, 30, 30, 0.5),      # staged tile > 48 KB (opt-in smem)
+                                               (1, 21, 64, 64, 16, 16, 0.5),      # strong down-sampling: un-staged taps
+                                               (1, 20, 12, 9, 47, 35, 0.3)])      # generic class count, IEEE division by temp
 def test_stage12_against_oracle(B, C, h, w, H, W, temp):
     import css_b200
     from css_b200 import synth
