@@ -245,7 +245,7 @@ def workload_config(args, cfg):
                         f"-> crop {cfg['H']}x{cfg['W']}, Q={cfg['Q']}, Nn={cfg['Nn']}, temp={cfg['temp']}, strong={cfg['strong']} "
                         "(BASELINE configs[1] shape; four-stage path incl. rep-space label + fusion of configs[2])",
             "pixels_per_step_per_gpu": 2 * cfg["B"] * cfg["h"] * cfg["w"],
-            "parallelism": f"batch-sharded x{args.gpus}, all-reduce of [C,D+1] class sums|counts",
+            "parallelism": f"batch-sharded x{args.gpus}, one sum of the [C,D+1] class sums|counts block per step",
             "l2": "no explicit flush: per-step working set (rep_u + rep_all + pixel-major copy + grad_rep ~ 400 MB) exceeds the 126 MB L2"}
 
 
@@ -477,7 +477,10 @@ def main():
             "data": "synthetic", "config": workload_config(args, cfg), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": float(t_e2e.item()) / args.e2e_steps, "steps": args.e2e_steps},
-            "gpu_launches": int(launches) * world, "launch_mode": "cuda_graph" if graph is not None else "eager", "clocks": clocks, "loss": loss_value, "present_classes": V, "scored_classes": v_eff,
+            "gpu_launches": int(launches) * world, "launch_mode": "cuda_graph" if graph is not None else "eager",
+            "exchange": {"peer": "css_stats_allreduce over NVLink peer memory (one launch, rank-ordered sum)",
+                         "nccl": "torch.distributed all_reduce", "none": "single process"}[crit.exchange_mode()],
+            "clocks": clocks, "loss": loss_value, "present_classes": V, "scored_classes": v_eff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

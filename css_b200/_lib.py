@@ -42,6 +42,13 @@ SIGNATURES = {
     "css_atl_blocks": (c_int, [c_int, c_int]),
     "css_atl_forward": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "css_atl_backward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
+    "css_comm_bytes": (ctypes.c_size_t, [c_int]),
+    "css_comm_alloc": (c_int, [c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "css_comm_free": (c_int, [P]),
+    "css_comm_export": (c_int, [P, ctypes.c_char_p]),
+    "css_comm_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "css_comm_close": (c_int, [P]),
+    "css_stats_allreduce": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "css_aug_index": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
     "css_aug_maps": (c_int, [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "css_cut_mix": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),

@@ -8,6 +8,8 @@ two classes are present).  Differences, all opt-in or invisible to callers:
   * sampling uses a device Philox stream; `forward(..., _indices=(anchor_idx, neg_idx))` feeds recorded draws
     (e.g. the reference's) for bit-exact verification.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -74,7 +76,7 @@ class _ContrastFn(torch.autograd.Function):
         rows_dt = _lib.DTYPE_BF16 if rows.dtype == torch.bfloat16 else _lib.DTYPE_F32
         check(lib.css_class_stats(ptr(rows), rows_dt, ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
                                   ptr(ws.class_stats), st), "css_class_stats")
-        allreduce_class_stats(ws.class_stats, mod.process_group)
+        mod._exchange(ws.class_stats, C, D, dev)
         check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
                                 float(mod.temp), C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
         if mod.sync_prototypes and dist.is_initialized() and dist.get_world_size(mod.process_group) > 1:
@@ -125,7 +127,7 @@ class Contrast_Loss(nn.Module):
     """Same constructor and forward as the reference's Contrast_Loss (loss.py:66-75)."""
 
     def __init__(self, num_queries, num_negatives, temp=0.5, mean=False, strong_threshold=0.97, alpha=0.99,
-                 seed=None, process_group=None, sync_prototypes=False):
+                 seed=None, process_group=None, sync_prototypes=False, exchange=None):
         super().__init__()
         self.temp = temp
         self.mean = mean                      # unused by the reference as well (loss.py:70)
@@ -135,6 +137,12 @@ class Contrast_Loss(nn.Module):
         self.alpha = alpha
         self.process_group = process_group
         self.sync_prototypes = sync_prototypes   # extension, default off: the reference lets per-rank prototypes drift
+        # how the [C, D+1] class statistics are summed over ranks: "peer" = css_stats_allreduce over NVLink peer memory
+        # (one node), "nccl" = dist.all_reduce, "auto" = peer when every rank can map every other rank's buffer, else nccl
+        self.exchange = exchange or os.environ.get("CSS_B200_EXCHANGE", "auto")
+        if self.exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self._reducer = None
         self._seed = seed
         self._step = 0
         self._counter = None
@@ -164,6 +172,27 @@ class Contrast_Loss(nn.Module):
             if dist.is_available() and dist.is_initialized():
                 self._seed ^= 0x9E3779B97F4A7C15 * (dist.get_rank() + 1) & (2 ** 63 - 1)
         return self._seed & (2 ** 64 - 1), 0
+
+    def _exchange(self, class_stats, C, D, device):
+        """The one exchange step of the path (loss.py:77-81,102 in the reference: two all_gathers of whole maps)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) <= 1:
+            return class_stats
+        if self.exchange != "nccl" and self._reducer is None:
+            from .comm import PeerStatsReducer
+            self._reducer = PeerStatsReducer(device, self.process_group)       # collective: first forward of every rank
+            if not self._reducer.ok and self.exchange == "peer":
+                raise RuntimeError("css_b200: exchange='peer' but the ranks cannot map each other's memory (CUDA IPC)")
+        if self._reducer is not None and self._reducer.ok:
+            return self._reducer.allreduce(class_stats, C, D)
+        return allreduce_class_stats(class_stats, self.process_group)
+
+    def exchange_mode(self):
+        """'peer', 'nccl' or 'none' (single process / not used yet): what the last forward used."""
+        if self._reducer is not None and self._reducer.ok:
+            return "peer"
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            return "nccl"
+        return "none"
 
     def _workspace(self, B2, C, D, h, w, device):
         key = (B2, C, D, h, w, self.num_queries, self.num_negatives, str(device))

@@ -221,6 +221,26 @@ int css_cut_mix(const float* image, const int64_t* label_a, const int64_t* label
                 float* out_image, int64_t* out_label_a, int64_t* out_label_b, float* out_conf_a, float* out_conf_b,
                 void* stream);
 
+/* ---- the exchange step over NVLink peer memory -----------------------------------------------------------------
+ * Sum of every rank's class_stats [C, D+1] block over the ranks of ONE node, in rank order (bit-identical on all ranks).
+ * Replaces concat_all_gather of rep / label (loss.py:77,81; ddp_model.py:241-250) and, on one node, the NCCL all-reduce.
+ *   css_comm_alloc  : cudaMalloc + zero a communication buffer for `world` ranks (css_comm_bytes(world) bytes)
+ *   css_comm_export : 64-byte CUDA IPC handle of the own buffer (HOST pointer) -- exchanged by the caller (e.g. all_gather_object)
+ *   css_comm_open   : map a peer's buffer from its handle; css_comm_close unmaps it; css_comm_free releases the own buffer
+ *   css_stats_allreduce: class_stats (device, in place) <- sum over ranks.  peer_buffers: DEVICE array of `world` device
+ *                     pointers, entry r = rank r's buffer as mapped in this process (entry `rank` = local_buffer).  One launch,
+ *                     no host synchronisation, CUDA-graph capturable; every rank must make the same sequence of calls.  A peer
+ *                     that does not arrive within 2 s turns the result into NaN instead of hanging the GPU.
+ */
+size_t css_comm_bytes(int world);
+int css_comm_alloc(int world, void** buffer);
+int css_comm_free(void* buffer);
+int css_comm_export(void* buffer, unsigned char* handle64);
+int css_comm_open(const unsigned char* handle64, void** peer_buffer);
+int css_comm_close(void* peer_buffer);
+int css_stats_allreduce(float* class_stats, void* local_buffer, void* const* peer_buffers, int rank, int world, int C, int D,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

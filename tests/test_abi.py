@@ -13,7 +13,7 @@ def header_functions():
     src = open(os.path.join(ROOT, "include", "css_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|unsigned\s+long\s+long|const\s+char\s*\*)\s+(css_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(?:int|size_t|unsigned\s+long\s+long|const\s+char\s*\*)\s+(css_\w+)\s*\(([^)]*)\)\s*;", src):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
     return out
