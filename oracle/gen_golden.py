@@ -275,6 +275,47 @@ def cut_case(name, *, maps, mode, B, C, H, W, seed):
     print(f"  {name}: boxes {boxes.tolist()}")
 
 
+def _cut_world2_worker(rank, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    load_reference()
+    import generalframeworks.dataset_helpers.VOC as V
+    image, l1, _, c1, c2 = _aug_inputs(3, 21, 33, 37, 300 + rank, True)
+    _seed_all(31)                                     # the scripts seed every rank alike (args.seed)
+    r = V.generate_cut_gather_2(image.clone(), l1.clone(), c1.clone(), c2.clone(), mode="cutmix")
+    out[rank] = dict(image=_np(image), label0=_np(l1).astype(np.int16), conf0=_np(c1), conf1=_np(c2), out_image=_np(r[0]),
+                     out_label0=_np(r[1]).astype(np.int16), out_conf0=_np(r[2]), out_conf1=_np(r[3]))
+    dist.destroy_process_group()
+
+
+def cut_world2_case(name):
+    """generate_cut_gather_2 of the reference on a TWO-process gloo group (VOC.py:393-434): pins that the partner index
+    (i + 1) % batch_size lands in rank 0's slice of the gathered batch and that every rank draws boxes for all gathered images."""
+    import torch.multiprocessing as mp
+    from css_b200 import aug
+    from oracle import css_oracle as O
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_cut_world2_worker, args=(29641, out), nprocs=2, join=True)
+    d = dict(seed=31, mode="cutmix")
+    B, _, H, W = out[0]["image"].shape
+    for rank in (0, 1):
+        _seed_all(31)
+        boxes = np.asarray([aug.draw_cut_box(H, W, 2) for _ in range(2 * B)], np.int32)[rank * B:(rank + 1) * B]
+        own, r0 = out[rank], out[0]
+        o = O.cut_mix(own["image"], [own["label0"].astype(np.int64)], [own["conf0"], own["conf1"]], "cutmix", boxes=boxes,
+                      partner=(r0["image"], [r0["label0"].astype(np.int64)], [r0["conf0"], r0["conf1"]]))
+        assert np.array_equal(o[0], own["out_image"]) and np.array_equal(o[1][0], own["out_label0"].astype(np.int64))
+        assert np.array_equal(o[2][0], own["out_conf0"]) and np.array_equal(o[2][1], own["out_conf1"])
+        d[f"r{rank}_boxes"] = boxes
+        for k, v in own.items():
+            d[f"r{rank}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"  {name}: ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     D = 256
@@ -330,6 +371,7 @@ def main():
     cut_case("cut_cutmix_3", maps=3, mode="cutmix", B=2, C=19, H=30, W=30, seed=22)
     cut_case("cut_cutout_1", maps=1, mode="cutout", B=3, C=21, H=33, W=37, seed=23)
     cut_case("cut_classmix_2", maps=2, mode="classmix", B=3, C=21, H=33, W=37, seed=24)
+    cut_world2_case("cut_cutmix_2_world2")
 
 
 if __name__ == "__main__":

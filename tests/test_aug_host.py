@@ -12,6 +12,7 @@ from tests.helpers import load_golden
 
 AUG = ["aug_t2_scale", "aug_t2_flip", "aug_t3_city", "aug_t1_ori"]
 CUT = ["cut_cutmix_2", "cut_cutmix_3", "cut_cutout_1", "cut_classmix_2"]
+CUT_WORLD2 = "cut_cutmix_2_world2"          # generate_cut_gather_2 of the reference on a two-process group
 
 
 def seed_all(seed):
@@ -52,6 +53,25 @@ def test_oracle_cut_mix_vs_reference(name):
         np.testing.assert_array_equal(a, b.astype(np.int64))
     for a, b in zip(o_conf, ref_c):
         np.testing.assert_array_equal(a, b)
+
+
+def test_oracle_cut_mix_two_ranks_vs_reference():
+    """On more than one rank the reference's partner (i + 1) % batch_size is an image of RANK 0 and every rank draws a box for
+    every gathered image (VOC.py:393-434 run on a two-process gloo group when the bundle was recorded)."""
+    from css_b200 import aug
+    g = load_golden(CUT_WORLD2)
+    B, _, H, W = g["r0_image"].shape
+    part = (g["r0_image"], [g["r0_label0"].astype(np.int64)], [g["r0_conf0"], g["r0_conf1"]])
+    for rank in (0, 1):
+        seed_all(int(g["seed"]))
+        boxes = np.asarray([aug.draw_cut_box(H, W, 2) for _ in range(2 * B)])[rank * B:(rank + 1) * B]
+        np.testing.assert_array_equal(boxes, g[f"r{rank}_boxes"])
+        o = O.cut_mix(g[f"r{rank}_image"], [g[f"r{rank}_label0"].astype(np.int64)], [g[f"r{rank}_conf0"], g[f"r{rank}_conf1"]],
+                      "cutmix", boxes=boxes, partner=part)
+        np.testing.assert_array_equal(o[0], g[f"r{rank}_out_image"])
+        np.testing.assert_array_equal(o[1][0], g[f"r{rank}_out_label0"].astype(np.int64))
+        np.testing.assert_array_equal(o[2][0], g[f"r{rank}_out_conf0"])
+        np.testing.assert_array_equal(o[2][1], g[f"r{rank}_out_conf1"])
 
 
 def test_pil_nearest_table_matches_pillow():
