@@ -4,7 +4,7 @@
 #include "css_common.cuh"
 
 // -------------------------------------------------------------------------------------------------------------------
-// Slab path.  CTA (g, b) owns every G-th 64 KB slab of image b's gradient (the image is one contiguous, 16-byte aligned
+// Slab path.  CTA (g, b) owns every G-th 32 KB slab of image b's gradient (the image is one contiguous, 16-byte aligned
 // run of 256*h*w floats).  It first lists the anchors that lie in image b (one scan of the anchor ids, a few hundred
 // hits, kept in shared memory), then builds each of its slabs in shared memory -- zero fill, shared-memory atomics for
 // the listed anchors' channels that fall inside (anchor pixel s touches element d*hw + s of the image for every channel
