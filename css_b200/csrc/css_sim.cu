@@ -57,7 +57,8 @@ __device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) {
 #define SM_WARPS 4
 #define SM_MINB 4
 
-template <int NG, bool ROWS, typename T>
+// T1: the last class group holds ONE class (C = 4 NG - 3, e.g. VOC's 21): one scalar FMA instead of two packed ones per pixel
+template <int NG, bool ROWS, typename T, bool T1 = false>
 __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const T* __restrict__ rep, const float* __restrict__ scratch,
                                                                          int hw, int N, int C, int mode, float temp,
                                                                          float* __restrict__ out, T* __restrict__ rows,
@@ -153,12 +154,18 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
                 if (NG > 0) {
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        const float4 q = myp[(d0 + u) * NGA + g];
+                        if (T1 && g == NG - 1) {
+                            const float q1 = reinterpret_cast<const float*>(myp + (d0 + u) * NGA + g)[0];
 #pragma unroll
-                        for (int j = 0; j < SM_PPT; ++j) {
-                            const float2 vv = make_float2(v[u][j], v[u][j]);
-                            acc[j][2 * g + 0] = __ffma2_rn(vv, make_float2(q.x, q.y), acc[j][2 * g + 0]);
-                            acc[j][2 * g + 1] = __ffma2_rn(vv, make_float2(q.z, q.w), acc[j][2 * g + 1]);
+                            for (int j = 0; j < SM_PPT; ++j) acc[j][2 * g].x = fmaf(v[u][j], q1, acc[j][2 * g].x);
+                        } else {
+                            const float4 q = myp[(d0 + u) * NGA + g];
+#pragma unroll
+                            for (int j = 0; j < SM_PPT; ++j) {
+                                const float2 vv = make_float2(v[u][j], v[u][j]);
+                                acc[j][2 * g + 0] = __ffma2_rn(vv, make_float2(q.x, q.y), acc[j][2 * g + 0]);
+                                acc[j][2 * g + 1] = __ffma2_rn(vv, make_float2(q.z, q.w), acc[j][2 * g + 1]);
+                            }
                         }
                     }
                 }
@@ -173,8 +180,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
                 if (NG > 0) {
 #pragma unroll
                     for (int i = 0; i < 2 * NG; ++i) {
+                        if (T1 && i == 2 * NG - 1) continue;                       // dead slots of the one-class tail
                         acc[j][i].x += __shfl_xor_sync(0xffffffffu, acc[j][i].x, o);
-                        acc[j][i].y += __shfl_xor_sync(0xffffffffu, acc[j][i].y, o);
+                        if (!(T1 && i == 2 * NG - 2)) acc[j][i].y += __shfl_xor_sync(0xffffffffu, acc[j][i].y, o);
                     }
                 }
             }
@@ -218,14 +226,14 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
     }
 }
 
-template <int NG, bool ROWS, typename T>
+template <int NG, bool ROWS, typename T, bool T1 = false>
 static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
                             T* rows, float* norms, cudaStream_t st) {
     constexpr int WP = (32 / SM_KS) * SM_PPT;
     const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
     const int cap = css_cached_sm_count() * SM_MINB;
-    rep_pass_kernel<NG, ROWS, T><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out, rows,
-                                                                                        norms);
+    rep_pass_kernel<NG, ROWS, T, T1><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out,
+                                                                                            rows, norms);
 }
 
 template <bool ROWS, typename T>
@@ -237,7 +245,10 @@ static void dispatch_rep_pass(int ng, const T* rep, const float* scratch, int hw
         case 3: launch_rep_pass<3, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
         case 4: launch_rep_pass<4, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
         case 5: launch_rep_pass<5, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
-        case 6: launch_rep_pass<6, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
+        case 6:
+            if (C == 21) launch_rep_pass<6, ROWS, T, true>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st);   // VOC
+            else launch_rep_pass<6, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st);
+            break;
         case 7: launch_rep_pass<7, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
         default: launch_rep_pass<8, ROWS, T>(rep, scratch, hw, N, C, mode, temp, out, rows, norms, st); break;
     }
