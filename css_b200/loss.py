@@ -79,6 +79,7 @@ class _ContrastFn(torch.autograd.Function):
         mod._exchange(ws.class_stats, C, D, dev)
         check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
                                 float(mod.temp), C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
+        torch.autograd.graph.increment_version(prototypes)     # updated in place through the raw pointer: tell autograd
         if mod.sync_prototypes and dist.is_initialized() and dist.get_world_size(mod.process_group) > 1:
             dist.broadcast(prototypes, src=dist.get_global_rank(mod.process_group, 0) if mod.process_group else 0,
                            group=mod.process_group)

@@ -417,7 +417,9 @@ def test_tiny_and_ragged_shapes(B2, C, h, w, Q, Nn):
     kw = dict(num_queries=Q, num_negatives=Nn, temp=0.5, strong_threshold=0.7, alpha=0.99)
     crit = css_b200.Contrast_Loss(seed=3, **kw).cuda()
     protos = torch.zeros(C, 256).cuda()
+    version = protos._version
     loss, grad = run_gpu(crit, rep, label, mask, prob, protos)
+    assert protos._version > version                # the in-place prototype update is visible to autograd's version counter
     sel = crit.selection()
     a, n = crit.sample_indices(3, 0)
     slots = scored_slots(sel)
