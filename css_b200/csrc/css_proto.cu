@@ -45,30 +45,56 @@ __global__ void __launch_bounds__(CSS_D) class_cdf_kernel(const float* __restric
         return;
     }
     const int ck = meta[CSS_META_CLS_OF_SLOT + k];
-    float a[CSS_D / 32];
+    // warp w scores the other classes i = w, w + 8, w + 16, w + 24 (V - 1 <= 31): their class ids first, then all their rows, so
+    // the warp pays one dependent pair of L2 round trips instead of one pair per class
+    constexpr int NW = CSS_D / 32, PER = CSS_CMAX / NW;
+    int cj[PER];
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+        const int i = warp + t * NW;
+        cj[t] = (i < V - 1) ? meta[CSS_META_CLS_OF_SLOT + (k + 1 + i) % V] : ck;
+    }
+    float a[CSS_D / 32], b[PER][CSS_D / 32];
 #pragma unroll
     for (int e = 0; e < CSS_D / 32; ++e) a[e] = proto_hat[ck * CSS_D + lane + 32 * e];
-    for (int i = warp; i < V - 1; i += CSS_D / 32) {
-        const int cj = meta[CSS_META_CLS_OF_SLOT + (k + 1 + i) % V];
+#pragma unroll
+    for (int t = 0; t < PER; ++t)
+#pragma unroll
+        for (int e = 0; e < CSS_D / 32; ++e) b[t][e] = proto_hat[cj[t] * CSS_D + lane + 32 * e];
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+        const int i = warp + t * NW;
         float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < CSS_D / 32; ++e) s = fmaf(a[e], proto_hat[cj * CSS_D + lane + 32 * e], s);
+        for (int e = 0; e < CSS_D / 32; ++e) s = fmaf(a[e], b[t][e], s);
         s = warp_sum(s);
-        if (lane == 0) sim[i] = __fdiv_rn(s, temp);
+        if (lane == 0 && i < V - 1) sim[i] = __fdiv_rn(s, temp);
     }
     __syncthreads();
-    if (d == 0) {
-        float m = -INFINITY;
-        for (int i = 0; i < V - 1; ++i) m = fmaxf(m, sim[i]);
+    if (warp == 0) {
+        // lane i owns class i: max, exp and the division run in parallel; the two running sums keep their sequential order
+        // (lane 0), so the table is bit-identical to a single-thread evaluation
+        const bool live = lane < V - 1;
+        float v = live ? sim[lane] : -INFINITY, m = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float ex = live ? expf(v - m) : 0.f;
+        if (live) sim[lane] = ex;
+        __syncwarp();
         float tot = 0.f;
-        for (int i = 0; i < V - 1; ++i) {
-            sim[i] = expf(sim[i] - m);
-            tot += sim[i];
-        }
-        float run = 0.f;
-        for (int i = 0; i < CSS_CMAX; ++i) {
-            if (i < V - 1) run += __fdiv_rn(sim[i], tot);
-            cdf[k * CSS_CMAX + i] = (i < V - 2) ? run : 1.f;                 // last bin absorbs rounding
+        if (lane == 0)
+            for (int i = 0; i < V - 1; ++i) tot += sim[i];
+        tot = __shfl_sync(0xffffffffu, tot, 0);
+        const float pr = live ? __fdiv_rn(ex, tot) : 0.f;
+        __syncwarp();
+        sim[lane] = pr;
+        __syncwarp();
+        if (lane == 0) {
+            float run = 0.f;
+            for (int i = 0; i < CSS_CMAX; ++i) {
+                if (i < V - 1) run += sim[i];
+                cdf[k * CSS_CMAX + i] = (i < V - 2) ? run : 1.f;             // last bin absorbs rounding
+            }
         }
     }
 }

@@ -114,24 +114,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) select_scan_kernel(int32_t* __re
         is_last = (atomicAdd(meta + CSS_META_TICKET, 1) == 2 * C - 1);
     }
     __syncthreads();
-    if (is_last && tid == 0) {
+    if (is_last && tid < 32) {
+        // the last CTA's first warp builds the slot tables: lane c owns class c, so the per-class counts are fetched in ONE
+        // round trip (a single thread walking 32 volatile words paid ~32 dependent L2 latencies)
         __threadfence();
-        volatile int32_t* vm = meta;
-        int V = 0;
-        for (int c = 0; c < CSS_CMAX; ++c) {
-            if (c >= C) {
-                vm[CSS_META_N_VALID + c] = 0;
-                vm[CSS_META_N_HARD + c] = 0;
-            }
-            if (c < C && vm[CSS_META_N_VALID + c] > 0) {         // classes with no local valid pixel are skipped (loss.py:96-97)
-                vm[CSS_META_CLS_OF_SLOT + V] = c;
-                vm[CSS_META_SLOT_OF_CLS + c] = V++;
-            } else {
-                vm[CSS_META_SLOT_OF_CLS + c] = -1;
-            }
+        const int c = tid;
+        int nv = 0;
+        if (c < C) {
+            nv = *((volatile int32_t*)meta + CSS_META_N_VALID + c);
+        } else {
+            meta[CSS_META_N_VALID + c] = 0;
+            meta[CSS_META_N_HARD + c] = 0;
         }
-        for (int k = V; k < CSS_CMAX; ++k) vm[CSS_META_CLS_OF_SLOT + k] = -1;
-        vm[CSS_META_V] = V;
+        const unsigned present = __ballot_sync(0xffffffffu, c < C && nv > 0);    // classes with no local valid pixel are skipped (loss.py:96-97)
+        const int V = __popc(present);
+        if ((present >> c) & 1u) {
+            const int slot = __popc(present & ((1u << c) - 1u));
+            meta[CSS_META_CLS_OF_SLOT + slot] = c;
+            meta[CSS_META_SLOT_OF_CLS + c] = slot;
+        } else {
+            meta[CSS_META_SLOT_OF_CLS + c] = -1;
+        }
+        if (c >= V) meta[CSS_META_CLS_OF_SLOT + c] = -1;
+        if (c == 0) meta[CSS_META_V] = V;
     }
 }
 
