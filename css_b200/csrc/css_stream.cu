@@ -4,7 +4,7 @@
 // resident).
 //
 // Layout: css_class_blocks(N) CTAs of 64 threads, each owning a contiguous run of pixels; thread t owns channels
-// 4t..4t+3 (one 128-bit load per row, 1 KB per CTA per pixel, 4 rows in flight).  Class sums accumulate in registers
+// 4t..4t+3 (one 128-bit load per row, 1 KB per CTA per pixel, 8 rows in flight).  Class sums accumulate in registers
 // along runs of equal class sets (segmentation maps are blocky) and spill to the CTA's own [C][256] slice of `partials`
 // only when the set changes; a second kernel adds the slices of the CTAs that touched a class in CTA order: no atomics,
 // bit-reproducible.
@@ -44,25 +44,33 @@ __global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const RT* __rest
     float4* part = partials + (size_t)blockIdx.x * C * (CSS_D / 4) + t;
     float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t run_bits = 0, seen = 0;
-    for (int p0 = p_begin; p0 < p_end; p0 += 4) {
-        float4 v[4];
-        uint32_t b[4];
+    __shared__ uint32_t sb[CS_PIX];
+    for (int c0 = p_begin; c0 < p_end; c0 += CS_PIX) {
+        // the class sets of the next 64 pixels with one coalesced load; then 8 rows in flight per thread (the former
+        // bits -> row dependency per 4 pixels cost two chained round trips sixteen times per CTA)
+        const int len = min(CS_PIX, p_end - c0);
+        __syncthreads();
+        if (t < len) sb[t] = __ldg(valid_bits + c0 + t);
+        __syncthreads();
+        for (int i0 = 0; i0 < len; i0 += 8) {
+            float4 v[8];
+            uint32_t b[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = p0 + i < p_end;
-            b[i] = ok ? __ldg(valid_bits + p0 + i) : 0u;
-            v[i] = (ok && b[i]) ? row_f4(rows, (size_t)(p0 + i), t) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (b[i] != run_bits) {                          // CTA-uniform branch
-                const uint32_t rb = run_bits;
-                flush_run(part, rb, seen, run);
-                seen |= rb;
-                run = make_float4(0.f, 0.f, 0.f, 0.f);
-                run_bits = b[i];
+            for (int i = 0; i < 8; ++i) {
+                b[i] = (i0 + i < len) ? sb[i0 + i] : 0u;
+                v[i] = b[i] ? row_f4(rows, (size_t)(c0 + i0 + i), t) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            run.x += v[i].x; run.y += v[i].y; run.z += v[i].z; run.w += v[i].w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (b[i] != run_bits) {                          // CTA-uniform branch
+                    const uint32_t rb = run_bits;
+                    flush_run(part, rb, seen, run);
+                    seen |= rb;
+                    run = make_float4(0.f, 0.f, 0.f, 0.f);
+                    run_bits = b[i];
+                }
+                run.x += v[i].x; run.y += v[i].y; run.z += v[i].z; run.w += v[i].w;
+            }
         }
     }
     {
@@ -112,14 +120,13 @@ __global__ void __launch_bounds__(CR_DCH * CR_SEG) class_reduce_kernel(const flo
     const int i0 = min(seg * per, n), i1 = min(i0 + per, n);
     float acc = 0.f;
     int i = i0;
-    for (; i + 8 <= i1; i += 8) {
+    for (; i < i1; i += 8) {                       // predicated batches: a scalar tail would pay one L2 round trip per element
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = partials[((size_t)glist[i + u] * C + c) * CSS_D + d];
+        for (int u = 0; u < 8; ++u) v[u] = (i + u < i1) ? partials[((size_t)glist[i + u] * C + c) * CSS_D + d] : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += v[u];
     }
-    for (; i < i1; ++i) acc += partials[((size_t)glist[i] * C + c) * CSS_D + d];
     segsum[seg][dl] = acc;
     __syncthreads();
     if (seg == 0) {
