@@ -27,13 +27,17 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const flo
         const float m = __ldg(mask + p);
         const float* lp = label + (size_t)b * C * hw + s;
         const float* pp = prob + (size_t)b * C * hw + s;
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-            const float l = ldg_stream(lp + (size_t)c * hw);
-            if (__fmul_rn(l, m) != 0.f) {                       // valid_pixel = label * mask (loss.py:80), .bool() (:99,:111)
-                vb |= 1u << c;
-                if (__ldg(pp + (size_t)c * hw) < strong) hb |= 1u << c;   // prob < strong_threshold (loss.py:99)
-            }
+        // all C label planes of the pixel in flight at once, then the probabilities of its (normally single) valid class:
+        // two round trips per pixel instead of a label -> prob chain per group of four classes
+        float l[CSS_CMAX];
+#pragma unroll
+        for (int c = 0; c < CSS_CMAX; ++c) l[c] = (c < C) ? ldg_stream(lp + (size_t)c * hw) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CSS_CMAX; ++c)
+            if (__fmul_rn(l[c], m) != 0.f) vb |= 1u << c;       // valid_pixel = label * mask (loss.py:80), .bool() (:99,:111)
+        for (uint32_t bits = vb; bits; bits &= bits - 1) {
+            const int c = __ffs(bits) - 1;
+            if (__ldg(pp + (size_t)c * hw) < strong) hb |= 1u << c;       // prob < strong_threshold (loss.py:99)
         }
         valid_bits[p] = vb;
         hard_bits[p] = hb;
@@ -144,7 +148,9 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_scatter_kernel(const uint
                                                                       const int32_t* __restrict__ tile_off, int C, int N, int T,
                                                                       int32_t* __restrict__ valid_list, int32_t* __restrict__ hard_list) {
     __shared__ int wcnt[2][CSS_CMAX][CSS_SEL_TILE / 32];
+    __shared__ int toff[2 * CSS_CMAX];             // this tile's offsets of all 2C lists: one round trip, not one per class
     for (int i = threadIdx.x; i < 2 * CSS_CMAX * (CSS_SEL_TILE / 32); i += CSS_SEL_TILE) (&wcnt[0][0][0])[i] = 0;
+    if (threadIdx.x < 2 * C) toff[threadIdx.x] = tile_off[(size_t)threadIdx.x * T + blockIdx.x];
     __syncthreads();
     const int p = blockIdx.x * CSS_SEL_TILE + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,9 +180,9 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_scatter_kernel(const uint
             oh += wcnt[1][c][w2];
         }
         if ((vb >> c) & 1u)
-            valid_list[(size_t)c * N + tile_off[(size_t)c * T + blockIdx.x] + ov + __popc(bv & lt)] = p;
+            valid_list[(size_t)c * N + toff[c] + ov + __popc(bv & lt)] = p;
         if ((hb >> c) & 1u)
-            hard_list[(size_t)c * N + tile_off[(size_t)(C + c) * T + blockIdx.x] + oh + __popc(bh & lt)] = p;
+            hard_list[(size_t)c * N + toff[C + c] + oh + __popc(bh & lt)] = p;
     }
 }
 
