@@ -22,9 +22,10 @@ __global__ void __launch_bounds__(CSS_D) proto_ema_kernel(float* __restrict__ pr
     __shared__ float scratch[8];
     const int c = blockIdx.x, d = threadIdx.x;
     float p = protos[c * CSS_D + d];
+    const float s_d = stats[c * (CSS_D + 1) + d], s_n = stats[c * (CSS_D + 1) + CSS_D];    // in flight with p and meta, ahead of the barriers
     if (meta[CSS_META_N_VALID + c] > 0) {                                   // only classes present on THIS rank (loss.py:96-97)
         const float rowsum = block_sum_256(p, scratch);
-        const float mean = __fdiv_rn(stats[c * (CSS_D + 1) + d], stats[c * (CSS_D + 1) + CSS_D]);   // loss.py:102
+        const float mean = __fdiv_rn(s_d, s_n);                              // loss.py:102
         p = (rowsum == 0.f) ? mean                                           // first touch (loss.py:103-105)
                             : __fadd_rn(__fmul_rn(alpha, p), __fmul_rn(one_minus_alpha, mean));   // loss.py:108
         protos[c * CSS_D + d] = p;

@@ -486,8 +486,15 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
     __shared__ float part[8];
     const int V = meta[CSS_META_V];
     float s = 0.f;
-    if (V > 1)
-        for (int i = threadIdx.x; i < V * Q; i += 256) s += loss_kq[i];
+    if (V > 1) {
+        for (int i0 = threadIdx.x; i0 < V * Q; i0 += 256 * 8) {            // 8 loads in flight, added in index order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (i0 + u * 256 < V * Q) ? loss_kq[i0 + u * 256] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+    }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
     __syncthreads();
