@@ -5,6 +5,9 @@ Public surface (mirrors the reference's names for this path):
     Attention_Threshold_Loss                        generalframeworks/loss/loss.py:48-64   
     Model_ori_pseudo, Model_mix, Model_cross        generalframeworks/networks/ddp_model.py:8-239
     ops.cos_sim_map / proto_softmax_sim / pseudo_labels / rep_pseudo_label / cls_pseudo_label / mix_fuse / threshold_glue
+    aug.batch_transform{,_2,_3}, aug.generate_cut_gather{,_2,_3}     dataset_helpers/VOC.py:312-477 for the label / confidence maps
+                                                    (imported on demand: needs torchvision + Pillow)
+    comm.PeerStatsReducer                           the class-statistics exchange over NVLink peer memory (one node)
     install.install()                               monkey-patches an unmodified reference checkout
 Importing the package does not load the CUDA library; the first op call does, and raises if it is missing.
 """

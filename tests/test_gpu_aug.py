@@ -1,8 +1,6 @@
 """GPU parity of the augmentation hand-off: css_aug_index / css_aug_maps / css_cut_mix through the C ABI
 against the bundles recorded from the live reference (batch_transform_*, generate_cut_gather_*), and against the oracle at
 the VOC / CityScapes crop sizes.  Everything is byte / index work: the bar is exact equality."""
-import random
-
 import numpy as np
 import pytest
 import torch
