@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--cpu-budget-s", type=float, default=float(os.environ.get("CSS_CPU_BUDGET_S", 150)))
+    ap.add_argument("--cpu-budget-s", type=float, default=float(os.environ.get("CSS_CPU_BUDGET_S", 240)))
+    ap.add_argument("--no-gpu-eager-reference", action="store_true", help="skip the reference-on-this-GPU context line")
     return ap.parse_args()
 
 
@@ -131,10 +132,88 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def pin_to_gpu_numa_node(index):
+    """Moves this process onto the CPUs NVML reports as local to GPU `index` (so that the pinned staging buffers allocated next
+    are first-touched on that NUMA node) and returns what it did; the previous affinity is restored by unpin_cpu()."""
+    info = {"gpu": index, "cpus_before": len(os.sched_getaffinity(0)), "pinned": False}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        hnd = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        try:
+            info["numa_node"] = int(nv.nvmlDeviceGetNumaNodeId(hnd))
+        except Exception:
+            info["numa_node"] = None
+        usable = cpus & os.sched_getaffinity(0)
+        info["gpu_local_cpus"] = len(cpus)
+        if usable and usable != os.sched_getaffinity(0):
+            _AFFINITY_STACK.append(os.sched_getaffinity(0))
+            os.sched_setaffinity(0, usable)
+            info["pinned"] = True
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
+_AFFINITY_STACK = []
+
+
+def unpin_cpu():
+    if _AFFINITY_STACK:
+        os.sched_setaffinity(0, _AFFINITY_STACK.pop())
+
+
+_PROBE = None
+
+
+def run_probe(rows, n_warps, n_per_warp):
+    """Ceilings of the access patterns, measured live (tools/dev/css_probe.cu): {'l2_gather_gbs', 'copy_gbs'} or None."""
+    global _PROBE
+    import ctypes
+    import torch
+    path = os.path.join(ROOT, "tools", "dev", "libcss_probe.so")
+    if not os.path.exists(path) or rows.dtype != torch.float32:
+        return None
+    try:
+        if _PROBE is None:
+            _PROBE = ctypes.CDLL(path)
+            _PROBE.css_probe_gather_gbs.restype = ctypes.c_double
+            _PROBE.css_probe_gather_gbs.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+            _PROBE.css_probe_copy_gbs.restype = ctypes.c_double
+            _PROBE.css_probe_copy_gbs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+        torch.cuda.synchronize()
+        scratch = torch.zeros(4, device=rows.device)
+        n_per_warp = max(16, (n_per_warp // 16) * 16)
+        g = _PROBE.css_probe_gather_gbs(rows.data_ptr(), rows.shape[0], int(n_warps), int(n_per_warp), 3, scratch.data_ptr())
+        a = torch.empty(256 << 20, device=rows.device, dtype=torch.uint8)
+        b = torch.empty_like(a)
+        c = _PROBE.css_probe_copy_gbs(b.data_ptr(), a.data_ptr(), a.numel(), 5)
+        torch.cuda.synchronize()
+        return {"l2_gather_gbs": g if g > 0 else None, "copy_gbs": c if c > 0 else None}
+    except Exception as e:
+        sys.stderr.write(f"bench: probe failed ({e!r})\n")
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port (numpy restatement of the reference's CPU path) on the host cores
+# reference arm / cpu baseline on the host cores: the UNMODIFIED reference (oracle/ref_bench.py, `kind: "reference"`) when its
+# tree is on this box (baseline/_ref, CSS_REFERENCE_ROOT or /root/reference), otherwise the oracle port (numpy restatement,
+# `kind: "port"`).  The only place bench.py executes anything under oracle/.
 # ------------------------------------------------------------------------------------------------------------------
 _PROB_CACHE = {}
+
+
+def run_cpu(cfg, steps, warmup, budget_s, rank_inputs):
+    if os.environ.get("CSS_BENCH_CPU_KIND", "auto") != "port":
+        try:
+            from oracle import ref_bench
+            if ref_bench.available():
+                return ref_bench.run_cpu(cfg, rank_inputs, steps, warmup, budget_s)
+        except Exception as e:      # a broken copy of the reference must not take the bench down: say so and use the port
+            sys.stderr.write(f"bench: reference CPU arm unavailable ({e!r}); timing the oracle port instead\n")
+    return run_cpu_port(cfg, steps, warmup, budget_s, rank_inputs)
 
 
 def _cached_prob(inp, protos, temp, n_sub):
@@ -177,7 +256,7 @@ def cpu_path_step(cfg, inp, protos, b_sub, q_sub):
     return t_half - t0, t_prob, (t2 - t1)
 
 
-def run_cpu(cfg, steps, warmup, budget_s, rank_inputs):
+def run_cpu_port(cfg, steps, warmup, budget_s, rank_inputs):
     """Times the oracle port for `steps` steps after `warmup`, inside `budget_s` seconds by shrinking the per-step
     sample (teacher images, queries per class) and scaling the time back to the full step."""
     import numpy as np
@@ -218,7 +297,7 @@ def run_cpu(cfg, steps, warmup, budget_s, rank_inputs):
               f"{2 * B} images + loss fwd+bwd on the full batch with {q_sub} of {Q} queries/class (Nn={cfg['Nn']}); stage 1/2 and prob "
               f"times are scaled by B/{b_sub}; the loss time t is scaled as F + (t - F)*Q/{q_sub} with the calibrated per-step fixed "
               f"cost F = {fixed:.2f} s")
-    return dict(value=N / t_step, t_step=t_step, cores=cores, sample=sample)
+    return dict(value=N / t_step, t_step=t_step, cores=cores, sample=sample, kind="port")
 
 
 def reference_arm(args, cfg):
@@ -232,7 +311,7 @@ def reference_arm(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg),
-        "cpu_baseline": {"value": r["value"], "unit": "pixels/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "pixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -282,18 +361,23 @@ def main():
     crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=cfg["strong"], alpha=0.99,
                                   seed=3407 + rank).to(dev)
 
-    def step(t):
-        """one pass of the path on device-resident tensors `t`; returns (loss, grad_rep)"""
+    def step(t, rep_for_loss=None):
+        """one pass of the path on device-resident tensors `t`; returns (loss, grad_rep, maps the augmentation receives).
+        rep_for_loss: what DistributedDataParallel(find_unused_parameters=True) hands the loss instead of rep_all (a clone)."""
+        maps = ()
         if strategy == "ori":
-            css_b200.ops.cls_pseudo_label(t["pred_u"], (H, W))
+            conf, lab = css_b200.ops.cls_pseudo_label(t["pred_u"], (H, W))
             prob = t["prob_ori"]
+            maps = (lab, conf)
         else:
-            css_b200.ops.pseudo_labels(t["rep_u"], t["pred_u"], protos, temp, (H, W), fuse="mix" if strategy == "mix" else "none")
+            o = css_b200.ops.pseudo_labels(t["rep_u"], t["pred_u"], protos, temp, (H, W), fuse="mix" if strategy == "mix" else "none")
             prob = css_b200.ops.proto_softmax_sim(t["rep_all"], protos, temp)
-        rep = t["rep_all"].detach().requires_grad_(True)
+            maps = (o["fused"], o["conf_cls"], o["conf_rep"]) if strategy == "mix" else \
+                (o["label_cls"], o["label_rep"], o["conf_cls"], o["conf_rep"])
+        rep = (t["rep_all"] if rep_for_loss is None else rep_for_loss).detach().requires_grad_(True)
         loss = crit(rep, t["label"], t["mask"], prob, protos)
         (grad,) = torch.autograd.grad(loss, rep)
-        return loss, grad
+        return loss, grad, maps
 
     def barrier():
         if world > 1:
@@ -302,24 +386,47 @@ def main():
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        loss, grad = step(gpu)
+        loss, grad, _ = step(gpu)
     barrier()
     meta = crit.last["ws"].meta.cpu().numpy()
     V = int(meta[_lib.META_V])
     v_eff = sum(1 for k in range(V) if meta[_lib.META_N_HARD + meta[_lib.META_CLS_OF_SLOT + k]] > 0) if V > 1 else 0
     loss_value = float(loss.item())
 
+    # ---- the one exchange step, checked on the real GPUs (outside every timed region): peer-memory kernel == dist.all_reduce ----
+    exchange_check = None
+    if world > 1:
+        torch.manual_seed(1000 + rank)
+        blk = torch.randn(C, D + 1, device=dev)
+        ref_sum = blk.clone()
+        dist.all_reduce(ref_sum)                                     # NCCL
+        mine = blk.clone()
+        crit._exchange(mine, C, D, dev)                              # what Contrast_Loss.forward calls
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        exact = torch.zeros(C, D + 1, device=dev, dtype=torch.float64)
+        blocks = [torch.empty_like(blk) for _ in range(world)]
+        dist.all_gather(blocks, blk)
+        for b_ in blocks:
+            exact += b_.double()
+        exchange_check = {"mode": crit.exchange_mode(),
+                          "max_abs_diff_vs_nccl_all_reduce": float((mine - ref_sum).abs().max().item()),
+                          "max_abs_diff_vs_fp64_sum": float((mine.double() - exact).abs().max().item()),
+                          "bit_identical_on_all_ranks": bool(all(torch.equal(g_, gathered[0]) for g_ in gathered)),
+                          "block": [C, D + 1], "ranks": world}
+        barrier()
+
     # ---- one step captured as a CUDA graph (the library is capturable: no host sync, caller-owned buffers) -------------
-    def capture(tensors):
+    def capture(tensors, rep_for_loss=None):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                step(tensors)
+                step(tensors, rep_for_loss)
         torch.cuda.current_stream().wait_stream(side)
         with torch.cuda.graph(g):
-            out = step(tensors)
+            out = step(tensors, rep_for_loss)
         return g, out
 
     use_graph = not args.no_graph
@@ -350,6 +457,8 @@ def main():
         launches_per_step = lib.css_launch_count() - l0
         barrier()
     launches0 = lib.css_launch_count()
+    reducer = getattr(crit, "_reducer", None)
+    comm0 = reducer.stats() if (reducer is not None and reducer.ok) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -358,26 +467,82 @@ def main():
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    comm1 = reducer.stats() if comm0 is not None else None
     launches = lib.css_launch_count() - launches0 if graph is None else launches_per_step * args.steps
     clocks = sampler.stop()
-    if graph is not None:      # live CUDA-event timing of the dominant kernel, same stream, eager launches of the same steps
-        crit.score_events = []
-        for _ in range(min(args.steps, 50)):
-            step(gpu)
-        barrier()
+    # live CUDA-event timing of the kernels the roofline reports, on the launching stream, eager launches of the same steps
+    crit.score_events = []
+    css_b200.ops.rep_pass_events = []
+    for _ in range(min(args.steps, 50)):
+        step(gpu)
+    barrier()
     score_ms = [a.elapsed_time(b) for a, b in crit.score_events]
+    rep_ms = {}
+    for a, b, label in css_b200.ops.rep_pass_events:
+        rep_ms.setdefault(label, []).append(a.elapsed_time(b))
     crit.score_events = None
-    t_el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    css_b200.ops.rep_pass_events = None
+    t_all = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+    t_mine = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_el.item()) / args.steps
+        dist.all_gather(t_all, t_mine)
+    else:
+        t_all = [t_mine]
+    per_rank_ms = [float(t.item()) / args.steps for t in t_all]
+    ms_per_step = max(per_rank_ms)
     value = world * N / (ms_per_step * 1e-3)
+    multi = None
+    if world > 1:
+        wait_us = None
+        if comm0 is not None:
+            calls = max(comm1["calls"] - comm0["calls"], 1)
+            w_mine = torch.tensor([(comm1["wait_ns_total"] - comm0["wait_ns_total"]) / calls / 1e3], device=dev, dtype=torch.float64)
+            w_all = [torch.zeros_like(w_mine) for _ in range(world)]
+            dist.all_gather(w_all, w_mine)
+            wait_us = [round(float(x.item()), 2) for x in w_all]
+        s_ = sorted(per_rank_ms)
+        multi = {"per_rank_ms_per_step": {"min": s_[0], "median": s_[len(s_) // 2], "max": s_[-1]},
+                 "exchange_wait_us_per_step_by_rank": wait_us,
+                 "note": "every rank times the same K steps with its own events; the step time reported is the max; "
+                         "exchange_wait = time the peer-memory kernel spent waiting for the slowest rank's block (rank skew)"}
 
-    # ---- e2e: host buffers, H2D of every input + D2H of the loss inside the timed region -----------------------------------
+    # ---- the step as the UNMODIFIED scripts drive it: DistributedDataParallel(find_unused_parameters=True) clones rep_all, the
+    # loss verifies the carried rows on the device (css_rows_refresh) instead of re-reading the map ---------------------------
+    ddp_line = None
+    if strategy != "ori":
+        rep_clone = gpu["rep_all"].clone()
+        try:
+            if use_graph:
+                g2, _ = capture(gpu, rep_clone)
+                run2 = g2.replay
+            else:
+                run2 = lambda: step(gpu, rep_clone)
+            for _ in range(3):
+                run2()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                run2()
+            e1.record()
+            barrier()
+            t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            ddp_line = {"ms_per_step": float(t2.item()) / args.steps, "rows_cache_mode": crit.last["rows_cache_mode"],
+                        "rows_stale_flag": int(crit.last["ws"].meta[_lib.META_ROWS_STALE].item()),
+                        "note": "same step with the loss fed a CLONE of rep_all (what DDP's output sink does, mix_label.py:77): the rows "
+                                "carried by prob are verified on the device, no second read of the map"}
+            g2 = None
+        except Exception as e:
+            ddp_line = {"error": repr(e)}
+
+    # ---- e2e: host buffers, H2D of every input + D2H of the loss and of the maps the augmentation receives -----------------
     keys = ["rep_u", "pred_u", "rep_all", "label", "mask"] if strategy != "ori" else ["pred_u", "rep_all", "label", "mask", "prob_ori"]
-    pinned = {k: host[k].pin_memory() for k in keys}
+    numa = pin_to_gpu_numa_node(physical_gpu_index(local_rank))          # before the pinned buffers are allocated (first touch)
+    pinned = {k: host[k].clone().pin_memory() for k in keys}
+    unpin_cpu()
     # two staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i; every step still uploads all
-    # of its inputs from pinned host memory and reads its loss back
+    # of its inputs from pinned host memory and reads its loss and label / confidence maps back
     staged = [{k: torch.empty_like(gpu[k]) for k in keys} for _ in range(2)]
     for st_set in staged:
         for k in gpu:
@@ -395,6 +560,9 @@ def main():
         except Exception as e:
             sys.stderr.write(f"bench: e2e graph capture failed ({e!r}); eager\n")
             e2e_graphs = [None, None]
+    _, _, maps0 = step(staged[0])
+    host_maps = [torch.empty(m.shape, dtype=m.dtype).pin_memory() for m in maps0]
+    d2h = 4 + sum(m.numel() * m.element_size() for m in host_maps)
 
     def upload(i):
         s_ = i % 2
@@ -415,11 +583,13 @@ def main():
             torch.cuda.current_stream().wait_event(ready[s_])
             if e2e_graphs[s_] is not None:
                 e2e_graphs[s_][0].replay()
-                loss = e2e_graphs[s_][1][0]
+                loss, _, maps = e2e_graphs[s_][1]
             else:
-                loss, grad = step(staged[s_])
+                loss, grad, maps = step(staged[s_])
+            for hm, m in zip(host_maps, maps):      # what the reference flow ships to the host for the PIL augmentation
+                hm.copy_(m, non_blocking=True)
             done[s_].record()
-            float(loss.item())                # D2H read of the step's result (synchronises)
+            float(loss.item())                # D2H read of the step's result (synchronises; the map copies precede it in stream order)
 
     e2e_run(4)
     barrier()
@@ -432,8 +602,22 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * N / (float(t_e2e.item()) / args.e2e_steps * 1e-3)
+    # the H2D leg alone (same pinned buffers, same copy stream, nothing else running): what the host side can deliver per rank
+    barrier()
+    e0.record()
+    for _ in range(5):
+        with torch.cuda.stream(copy_stream):
+            for k in keys:
+                staged[0][k].copy_(pinned[k], non_blocking=True)
+    copy_stream.synchronize()
+    e1.record()
+    barrier()
+    t_h2d = torch.tensor([e0.elapsed_time(e1) / 5], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_h2d, op=dist.ReduceOp.MAX)
+    h2d_only_ms = float(t_h2d.item())
 
-    # ---- roofline of the dominant kernel (css_score_ce: per-query row gather + CE + d/d anchor) --------------------------
+    # ---- rooflines ------------------------------------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -442,44 +626,81 @@ def main():
     stream_b, gather_b = path_bytes(cfg, v_eff)
     score_avg_ms = sum(score_ms) / max(len(score_ms), 1)
     achieved = gather_b / (score_avg_ms * 1e-3) / 1e9 if score_avg_ms > 0 else 0.0
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "score_ce_traffic.json")
-    if os.path.exists(prof):
+    prof = {}
+    prof_path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(prof_path):
         try:
-            traffic = json.load(open(prof)).get(args.workload)
+            prof = json.load(open(prof_path)).get(args.workload, {})
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "score_ce_kernel (css_score_ce)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "dram_gbs": (traffic / (score_avg_ms * 1e-3) / 1e9) if (traffic and score_avg_ms > 0) else None,
-                "l2_served_frac": (1.0 - traffic / gather_b) if (traffic and gather_b) else None,
-                "algorithmic_bytes_per_launch": gather_b, "avg_launch_ms": score_avg_ms, "share_of_step": score_avg_ms / ms_per_step,
-                "note": "achieved counts LOGICAL 1 KB row gathers (SURVEY.md 8(d)); the 107 MB pixel-major copy is mostly L2 "
-                        "resident at this size, so frac > 1 is L2 service, not HBM: `traffic` (ncu dram bytes per launch) and "
-                        "`dram_gbs` say what really reached HBM; the kernel is bound by the L2->SM gather path (~17-19 TB/s "
-                        "measured ceiling for random 1 KB rows, tools/dev/dev_gather.cu)",
+            prof = {}
+    traffic = prof.get("score_ce_kernel")
+    # ceiling of the access pattern, measured live on this device with the step's own pixel-major copy as the table
+    probe = run_probe(crit.last["rows"], v_eff * Q if v_eff else Q, Nn)
+    gather_peak = probe.get("l2_gather_gbs") if probe else None
+    roofline = {"bound": "l2_gather", "kernel": "score_ce_kernel (css_score_ce)", "achieved": achieved,
+                "peak": gather_peak, "unit": "GB/s", "frac": (achieved / gather_peak) if gather_peak else None,
+                "peak_source": "measured live by tools/dev/css_probe.cu: random 1 KB-row gathers from this step's own pixel-major copy "
+                               f"({crit.last['rows'].numel() * crit.last['rows'].element_size() / 1e6:.0f} MB table), no math, best of 3 "
+                               "variants" if gather_peak else "probe library absent (tools/dev/libcss_probe.so)",
+                "traffic": traffic, "algorithmic_bytes_per_launch": gather_b, "avg_launch_ms": score_avg_ms,
+                "share_of_step": score_avg_ms / ms_per_step,
+                "hbm": {"peak": peak, "peak_source": peak_src,
+                        "dram_gbs": (traffic / (score_avg_ms * 1e-3) / 1e9) if (traffic and score_avg_ms > 0) else None,
+                        "dram_frac_of_hbm": (traffic / (score_avg_ms * 1e-3) / 1e9 / peak) if (traffic and score_avg_ms > 0) else None,
+                        "logical_over_hbm": achieved / peak,
+                        "l2_served_frac": (1.0 - traffic / gather_b) if (traffic and gather_b) else None},
+                "note": "the dominant kernel gathers one 1 KB row per (query, candidate) pair (SURVEY.md 8(d): V*Q*(Nn+1)*D*4 logical bytes); "
+                        "the table is mostly L2 resident, so the bound is the L2->SM gather path, not HBM: `achieved`/`peak` are logical "
+                        "gather GB/s against the live-measured ceiling of that pattern; `hbm` says what reached DRAM (ncu dram bytes "
+                        "per launch from profiles/kernel_traffic.json) and how the logical figure compares with measured HBM bandwidth",
                 "path": {"bytes_stream": stream_b, "bytes_gather": gather_b,
                          "achieved_gbs": (stream_b + gather_b) / (ms_per_step * 1e-3) / 1e9,
-                         "frac": (stream_b + gather_b) / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "frac_of_hbm": (stream_b + gather_b) / (ms_per_step * 1e-3) / 1e9 / peak,
                          "compulsory_gbs": stream_b / (ms_per_step * 1e-3) / 1e9,
-                         "compulsory_frac": stream_b / (ms_per_step * 1e-3) / 1e9 / peak}}
+                         "compulsory_frac_of_hbm": stream_b / (ms_per_step * 1e-3) / 1e9 / peak}}
+    # the HBM-bound streaming kernel: the student rep pass (one read of rep_all -> prob_all + pixel-major rows + norms)
+    roofline_hbm = None
+    if rep_ms.get("student"):
+        t_st = sum(rep_ms["student"]) / len(rep_ms["student"])
+        s_el = 4
+        alg = N * (D * s_el + 4 * C + D * s_el + 4)
+        tr = prof.get("rep_pass_student")
+        roofline_hbm = {"bound": "hbm", "kernel": "rep_pass_kernel<SOFTMAX, rows> (css_rep_pass, student; the timing includes the "
+                        "2 us prototype-preparation launch of the same call)", "achieved": alg / (t_st * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg / (t_st * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": tr,
+                        "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_st, "share_of_step": t_st / ms_per_step,
+                        "dram_frac_of_hbm": (tr / (t_st * 1e-3) / 1e9 / peak) if tr else None,
+                        "copy_gbs_live": probe.get("copy_gbs") if probe else None,
+                        "teacher_avg_launch_ms": (sum(rep_ms["teacher"]) / len(rep_ms["teacher"])) if rep_ms.get("teacher") else None}
 
     cpu = None
+    gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # one bounded sample of the same workload on the host cores (oracle port), ~10-30 s
+        # one bounded sample of the same workload on the host cores (the unmodified reference when it is on this box), ~10-30 s
         r = run_cpu(cfg, 1, 0, 25.0, host)
-        cpu = {"value": r["value"], "unit": "pixels/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = {"value": r["value"], "unit": "pixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        if not args.no_gpu_eager_reference:
+            try:      # context line: the same unmodified reference code, eager, on this GPU
+                from oracle import ref_bench
+                if ref_bench.available():
+                    gpu_eager = ref_bench.run_gpu_eager(cfg, host, steps=2, warmup=1, device=str(dev))
+            except Exception as e:
+                gpu_eager = {"error": repr(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, cfg), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": float(t_e2e.item()) / args.e2e_steps, "steps": args.e2e_steps},
+            "data": "synthetic", "config": workload_config(args, cfg), "roofline": roofline, "roofline_hbm_kernel": roofline_hbm,
+            "cpu_baseline": cpu, "reference_gpu_eager": gpu_eager,
+            "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t_e2e.item()) / args.e2e_steps, "steps": args.e2e_steps,
+                    "h2d_only_ms_per_step": h2d_only_ms, "h2d_only_gbs_per_rank": h2d / (h2d_only_ms * 1e-3) / 1e9, "host_numa": numa,
+                    "d2h": "loss scalar + the label / confidence maps the reference flow hands to the host-side augmentation"},
             "gpu_launches": int(launches) * world, "launch_mode": "cuda_graph" if graph is not None else "eager",
             "exchange": {"peer": "css_stats_allreduce over NVLink peer memory (one launch, rank-ordered sum)",
                          "nccl": "torch.distributed all_reduce", "none": "single process"}[crit.exchange_mode()],
+            "exchange_check": exchange_check, "multi_gpu": multi, "ddp_clone_step": ddp_line,
             "clocks": clocks, "loss": loss_value, "present_classes": V, "scored_classes": v_eff,
         }
         print(json.dumps(line), flush=True)

@@ -15,8 +15,10 @@ SIM_COS, SIM_SOFTMAX = 0, 1
 FUSE_NONE, FUSE_MIX = 0, 1
 LABEL_F32, LABEL_I64 = 0, 1
 CUT_CUTOUT, CUT_CUTMIX, CUT_CLASSMIX = 0, 1, 2
+UPDATE_LOCAL, UPDATE_GLOBAL = 0, 1
 META_WORDS = 256
 META_V, META_N_VALID, META_N_HARD, META_CLS_OF_SLOT, META_SLOT_OF_CLS = 0, 32, 64, 96, 128
+META_ROWS_STALE = 164
 CMAX = 32
 D = 256
 
@@ -32,9 +34,10 @@ SIGNATURES = {
     "css_select_tiles": (c_int, [c_int]),
     "css_select": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "css_rep_pass": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P]),
+    "css_rows_refresh": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
     "css_class_blocks": (c_int, [c_int]),
     "css_class_stats": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
-    "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, P, P, P]),
+    "css_proto_ema": (c_int, [P, P, P, c_float, c_float, c_float, c_int, c_int, c_int, P, P, P]),
     "css_sample": (c_int, [P, P, c_uint64, c_uint64, c_int, c_int, c_int, P, P, P]),
     "css_score_ce": (c_int, [P, c_int, P, P, P, P, P, P, P, P, c_uint64, c_uint64, P, c_int, c_int, c_int, c_int, c_int, c_float,
                              P, P, P, P, P]),
@@ -45,6 +48,9 @@ SIGNATURES = {
     "css_comm_bytes": (ctypes.c_size_t, [c_int]),
     "css_comm_alloc": (c_int, [c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "css_comm_free": (c_int, [P]),
+    "css_comm_set_timeout_ms": (c_int, [ctypes.c_ulonglong]),
+    "css_comm_timeouts": (c_int, [P]),
+    "css_comm_stats": (c_int, [P, ctypes.POINTER(ctypes.c_ulonglong)]),
     "css_comm_export": (c_int, [P, ctypes.c_char_p]),
     "css_comm_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "css_comm_close": (c_int, [P]),

@@ -28,6 +28,8 @@ class PeerStatsReducer:
         self.mapped = {}
         self.ok = False
         lib = _lib.load()
+        if os.environ.get("CSS_B200_COMM_TIMEOUT_S"):
+            check(lib.css_comm_set_timeout_ms(int(float(os.environ["CSS_B200_COMM_TIMEOUT_S"]) * 1000)), "css_comm_set_timeout_ms")
         handle = None
         with torch.cuda.device(self.device):
             buf = ctypes.c_void_p()
@@ -65,8 +67,24 @@ class PeerStatsReducer:
         else:
             self.close()
 
+    def timeouts(self):
+        """Calls that gave up waiting for a peer so far (read from pinned host memory: no synchronisation)."""
+        return _lib.load().css_comm_timeouts(self.local) if self.local is not None else 0
+
+    def stats(self):
+        """dict(calls, timeouts, wait_ns_total): blocking device read, for diagnostics outside timed regions."""
+        out = (ctypes.c_ulonglong * 3)()
+        with torch.cuda.device(self.device):
+            check(_lib.load().css_comm_stats(self.local, out), "css_comm_stats")
+        return dict(calls=int(out[0]), timeouts=int(out[1]), wait_ns_total=int(out[2]))
+
     def allreduce(self, class_stats, C, D):
         lib = _lib.load()
+        n = lib.css_comm_timeouts(self.local)
+        if n > 0:      # the step that timed out used this rank's local statistics; the ranks are out of step from here on
+            raise RuntimeError(f"css_b200: the peer-memory exchange timed out {n} time(s): a rank did not reach "
+                               "Contrast_Loss.forward in time (CSS_B200_COMM_TIMEOUT_S, default 600 s); the affected step "
+                               "updated the prototypes from rank-local statistics only")
         with torch.cuda.device(self.device):
             check(lib.css_stats_allreduce(ptr(class_stats), self.local, ptr(self.peer_table), self.rank, self.world, C, D, stream_ptr()),
                   "css_stats_allreduce")

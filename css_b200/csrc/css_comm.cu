@@ -6,7 +6,9 @@
 // peers).  One launch, one CTA:
 //   push   this rank's block is stored into slot[parity][rank] of EVERY peer's buffer (remote stores over NVLink),
 //   signal after a system-scope fence, flag[parity][rank] = epoch on every peer,
-//   wait   until the own buffer holds the flags of all ranks for this epoch (bounded spin),
+//   wait   until the own buffer holds the flags of all ranks for this epoch (bounded spin: css_comm_set_timeout_ms, default
+//          10 minutes like the NCCL watchdog; on expiry the block is left as the LOCAL statistics -- never poisoned -- and the
+//          event is counted in a host-visible status word that css_comm_timeouts() reads without synchronising),
 //   sum    the slots are added in RANK ORDER, so every rank gets bit-identical statistics (NCCL's order depends on the
 //          algorithm it picks) and the prototypes cannot drift apart between ranks.
 // The epoch lives in the buffer and is bumped by the kernel, so a captured CUDA graph replays correctly.  Slots alternate
@@ -19,13 +21,15 @@
 #define COMM_MAX_WORLD 16
 #define COMM_SLOT_FLOATS (CSS_CMAX * (CSS_D + 1))
 #define COMM_THREADS 1024
-#define COMM_TIMEOUT_NS 2000000000ull         // a peer that does not show up within 2 s poisons the result instead of hanging
+#define COMM_TIMEOUT_DEFAULT_MS 600000ull      // a rank may legitimately be seconds late (checkpoint write, loader respawn, GC)
 
 struct CommHeader {
     unsigned int flags[2][COMM_MAX_WORLD];
     unsigned int epoch;
-    unsigned int timeouts;                    // number of calls that gave up waiting (diagnostics)
-    unsigned int pad[30];
+    unsigned int timeouts;                    // number of calls that gave up waiting
+    unsigned int* host_status;                // pinned, mapped: [0] = timeouts, mirrored so the host can poll without a sync
+    unsigned long long wait_ns;               // total time the calls spent waiting for the slowest peer (css_comm_stats)
+    unsigned int pad[26];
 };
 static_assert(sizeof(CommHeader) == 256, "CommHeader layout");
 
@@ -44,13 +48,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 __global__ void __launch_bounds__(COMM_THREADS) stats_allreduce_kernel(float* __restrict__ class_stats, void* local, void* const* __restrict__ peers,
-                                                                       int rank, int world, int n) {
+                                                                       int rank, int world, int n, unsigned long long timeout_ns) {
     __shared__ unsigned int s_epoch;
     __shared__ int s_ok;
+    __shared__ unsigned long long s_wait;
     CommHeader* me = reinterpret_cast<CommHeader*>(local);
     if (threadIdx.x == 0) {
         s_epoch = me->epoch + 1;
         s_ok = 1;
+        s_wait = 0ull;
     }
     __syncthreads();
     const unsigned int epoch = s_epoch;
@@ -76,47 +82,113 @@ __global__ void __launch_bounds__(COMM_THREADS) stats_allreduce_kernel(float* __
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if (v == epoch) break;
-            if (global_ns() - t0 > COMM_TIMEOUT_NS) {
+            if (global_ns() - t0 > timeout_ns) {
                 s_ok = 0;
                 break;
             }
         } while (true);
+        atomicMax(&s_wait, global_ns() - t0);
     }
     __syncthreads();
     const bool ok = s_ok != 0;
-    for (int i = threadIdx.x; i < n; i += COMM_THREADS) {
-        float s = 0.f;
-        for (int p = 0; p < world; ++p) s += __ldcg(comm_slot(local, world, parity, p) + i);     // L2: the slots were written remotely
-        class_stats[i] = ok ? s : __int_as_float(0x7fc00000);
-    }
+    if (ok) {
+        for (int i = threadIdx.x; i < n; i += COMM_THREADS) {
+            float s = 0.f;
+            for (int p = 0; p < world; ++p) s += __ldcg(comm_slot(local, world, parity, p) + i);     // L2: the slots were written remotely
+            class_stats[i] = s;
+        }
+    }   // else: a peer never arrived -- class_stats keeps this rank's own statistics (a valid, rank-local prototype update)
     if (threadIdx.x == 0) {
         me->epoch = epoch;
-        if (!ok) me->timeouts += 1;
+        me->wait_ns += s_wait;
+        if (!ok) {
+            me->timeouts += 1;
+            if (me->host_status) {
+                *reinterpret_cast<volatile unsigned int*>(me->host_status) = me->timeouts;
+                __threadfence_system();
+            }
+        }
     }
 }
 
 extern "C" size_t css_comm_bytes(int world) { return (world >= 1 && world <= COMM_MAX_WORLD) ? comm_bytes(world) : 0; }
 
+// host-side registry of the buffers this process allocated: device buffer -> its pinned status word
+#define COMM_MAX_LOCAL 64
+static struct { void* dev; unsigned int* host; } g_comm[COMM_MAX_LOCAL];
+static unsigned long long g_timeout_ms = COMM_TIMEOUT_DEFAULT_MS;
+
+static int comm_find(void* buffer) {
+    for (int i = 0; i < COMM_MAX_LOCAL; ++i)
+        if (g_comm[i].dev == buffer) return i;
+    return -1;
+}
+
+extern "C" int css_comm_set_timeout_ms(unsigned long long ms) {
+    CSS_CHECK_ARG(ms > 0, CSS_E_ARG, "css_comm_set_timeout_ms: timeout must be positive");
+    g_timeout_ms = ms;
+    return 0;
+}
+
 extern "C" int css_comm_alloc(int world, void** buffer) {
     CSS_CHECK_ARG(buffer && world >= 1 && world <= COMM_MAX_WORLD, CSS_E_ARG, "css_comm_alloc: world must be in [1,%d]", COMM_MAX_WORLD);
+    const int slot = comm_find(nullptr);
+    CSS_CHECK_ARG(slot >= 0, CSS_E_SIZE, "css_comm_alloc: more than %d live communication buffers", COMM_MAX_LOCAL);
     void* p = nullptr;
+    unsigned int* hs = nullptr;
+    unsigned int* hs_dev = nullptr;
     cudaError_t e = cudaMalloc(&p, comm_bytes(world));
     if (e == cudaSuccess) e = cudaMemset(p, 0, comm_bytes(world));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&hs, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        memset(hs, 0, 64);
+        e = cudaHostGetDevicePointer((void**)&hs_dev, hs, 0);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&reinterpret_cast<CommHeader*>(p)->host_status, &hs_dev, sizeof(hs_dev), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (p) cudaFree(p);
+        if (hs) cudaFreeHost(hs);
         css_set_error("css_comm_alloc: %s", cudaGetErrorString(e));
         return (int)e;
     }
+    g_comm[slot].dev = p;
+    g_comm[slot].host = hs;
     *buffer = p;
     return 0;
 }
 
 extern "C" int css_comm_free(void* buffer) {
     if (!buffer) return 0;
+    const int slot = comm_find(buffer);
     cudaError_t e = cudaFree(buffer);
+    if (slot >= 0) {
+        if (g_comm[slot].host) cudaFreeHost(g_comm[slot].host);
+        g_comm[slot].dev = nullptr;
+        g_comm[slot].host = nullptr;
+    }
     if (e != cudaSuccess) { css_set_error("css_comm_free: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
+}
+
+// diagnostics of a local buffer: out[0] = completed calls (epoch), out[1] = timeouts, out[2] = total ns spent waiting for peers.
+// Reads device memory with a blocking copy: never call it inside a timed region.
+extern "C" int css_comm_stats(void* buffer, unsigned long long* out3_host) {
+    CSS_CHECK_ARG(buffer && out3_host && comm_find(buffer) >= 0, CSS_E_ARG, "css_comm_stats: not a buffer of css_comm_alloc");
+    CommHeader h;
+    cudaError_t e = cudaMemcpy(&h, buffer, sizeof(h), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { css_set_error("css_comm_stats: %s", cudaGetErrorString(e)); return (int)e; }
+    out3_host[0] = h.epoch;
+    out3_host[1] = h.timeouts;
+    out3_host[2] = h.wait_ns;
+    return 0;
+}
+
+// number of css_stats_allreduce calls on `buffer` that gave up waiting for a peer; reads pinned host memory, never synchronises
+extern "C" int css_comm_timeouts(void* buffer) {
+    const int slot = buffer ? comm_find(buffer) : -1;
+    CSS_CHECK_ARG(slot >= 0, CSS_E_ARG, "css_comm_timeouts: not a buffer of css_comm_alloc");
+    return (int)*reinterpret_cast<volatile unsigned int*>(g_comm[slot].host);
 }
 
 extern "C" int css_comm_export(void* buffer, unsigned char* handle64) {
@@ -153,7 +225,8 @@ extern "C" int css_stats_allreduce(float* class_stats, void* local_buffer, void*
     CSS_CHECK_ARG(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world, CSS_E_ARG, "css_stats_allreduce: bad rank %d / world %d",
                   rank, world);
     if (int e = css_check_dims(C, D)) return e;
-    stats_allreduce_kernel<<<1, COMM_THREADS, 0, (cudaStream_t)stream>>>(class_stats, local_buffer, peer_buffers, rank, world, C * (D + 1));
+    stats_allreduce_kernel<<<1, COMM_THREADS, 0, (cudaStream_t)stream>>>(class_stats, local_buffer, peer_buffers, rank, world, C * (D + 1),
+                                                                         g_timeout_ms * 1000000ull);
     CSS_CHECK_LAUNCH("css_stats_allreduce", 1);
     return 0;
 }

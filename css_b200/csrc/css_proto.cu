@@ -18,12 +18,15 @@ __device__ __forceinline__ float block_sum_256(float v, float* scratch) {
 // one CTA per class: mean / first-touch / EMA in place, then the normalised row for the scorer
 __global__ void __launch_bounds__(CSS_D) proto_ema_kernel(float* __restrict__ protos, const float* __restrict__ stats,
                                                           const int32_t* __restrict__ meta, float alpha, float one_minus_alpha,
-                                                          float* __restrict__ proto_hat) {
+                                                          int update_rule, float* __restrict__ proto_hat) {
     __shared__ float scratch[8];
     const int c = blockIdx.x, d = threadIdx.x;
     float p = protos[c * CSS_D + d];
     const float s_d = stats[c * (CSS_D + 1) + d], s_n = stats[c * (CSS_D + 1) + CSS_D];    // in flight with p and meta, ahead of the barriers
-    if (meta[CSS_META_N_VALID + c] > 0) {                                   // only classes present on THIS rank (loss.py:96-97)
+    // CSS_UPDATE_LOCAL: only classes present on THIS rank (loss.py:96-97); CSS_UPDATE_GLOBAL: every class any rank saw, so
+    // that ranks starting from equal prototypes stay bit-identical (the summed statistics are the same on every rank)
+    const bool touch = update_rule == CSS_UPDATE_GLOBAL ? (s_n > 0.f) : (meta[CSS_META_N_VALID + c] > 0);
+    if (touch) {
         const float rowsum = block_sum_256(p, scratch);
         const float mean = __fdiv_rn(s_d, s_n);                              // loss.py:102
         p = (rowsum == 0.f) ? mean                                           // first touch (loss.py:103-105)
@@ -101,10 +104,11 @@ __global__ void __launch_bounds__(CSS_D) class_cdf_kernel(const float* __restric
 }
 
 extern "C" int css_proto_ema(float* prototypes, const float* class_stats, const int32_t* meta, float alpha, float one_minus_alpha,
-                             float temp, int C, int D, float* proto_hat, float* class_cdf, void* stream) {
+                             float temp, int update_rule, int C, int D, float* proto_hat, float* class_cdf, void* stream) {
     CSS_CHECK_ARG(prototypes && class_stats && meta && proto_hat && class_cdf, CSS_E_ARG, "css_proto_ema: null pointer");
+    CSS_CHECK_ARG(update_rule == CSS_UPDATE_LOCAL || update_rule == CSS_UPDATE_GLOBAL, CSS_E_ARG, "css_proto_ema: bad update_rule %d", update_rule);
     if (int e = css_check_dims(C, D)) return e;
-    proto_ema_kernel<<<C, CSS_D, 0, (cudaStream_t)stream>>>(prototypes, class_stats, meta, alpha, one_minus_alpha, proto_hat);
+    proto_ema_kernel<<<C, CSS_D, 0, (cudaStream_t)stream>>>(prototypes, class_stats, meta, alpha, one_minus_alpha, update_rule, proto_hat);
     class_cdf_kernel<<<CSS_CMAX, CSS_D, 0, (cudaStream_t)stream>>>(proto_hat, meta, temp, class_cdf);
     CSS_CHECK_LAUNCH("css_proto_ema", 2);
     return 0;

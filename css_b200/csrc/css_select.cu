@@ -18,7 +18,10 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const flo
                                                                        int32_t* __restrict__ meta) {
     __shared__ int cnt[2 * CSS_CMAX];
     if (threadIdx.x < 2 * CSS_CMAX) cnt[threadIdx.x] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) meta[CSS_META_TICKET] = 0;      // ticket of the scan kernel's last-CTA election
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        meta[CSS_META_TICKET] = 0;           // ticket of the scan kernel's last-CTA election
+        meta[CSS_META_ROWS_STALE] = 0;       // raised by css_rows_refresh's comparison later in the same step
+    }
     __syncthreads();
     const int p = blockIdx.x * CSS_SEL_TILE + threadIdx.x;
     uint32_t vb = 0, hb = 0;

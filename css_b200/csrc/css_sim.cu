@@ -62,7 +62,8 @@ template <int NG, bool ROWS, typename T, bool T1 = false>
 __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const T* __restrict__ rep, const float* __restrict__ scratch,
                                                                          int hw, int N, int C, int mode, float temp,
                                                                          float* __restrict__ out, T* __restrict__ rows,
-                                                                         float* __restrict__ norms) {
+                                                                         float* __restrict__ norms, const int32_t* __restrict__ guard) {
+    if (guard != nullptr && *guard == 0) return;     // css_rows_refresh: the carried rows were verified, nothing to redo
     constexpr int DS = CSS_D / SM_KS;          // channels per slice
     constexpr int PL = 32 / SM_KS;             // pixel lanes per warp
     constexpr int WP = PL * SM_PPT;            // pixels per warp
@@ -228,12 +229,12 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
 
 template <int NG, bool ROWS, typename T, bool T1 = false>
 static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, int C, int mode, float temp, float* out,
-                            T* rows, float* norms, cudaStream_t st) {
+                            T* rows, float* norms, cudaStream_t st, const int32_t* guard = nullptr) {
     constexpr int WP = (32 / SM_KS) * SM_PPT;
     const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
     const int cap = css_cached_sm_count() * SM_MINB;
     rep_pass_kernel<NG, ROWS, T, T1><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out,
-                                                                                            rows, norms);
+                                                                                            rows, norms, guard);
 }
 
 template <bool ROWS, typename T>
@@ -292,6 +293,58 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
                            int D, int h, int w, int mode, float temp, float* out, void* stream) {
     CSS_CHECK_ARG(rep && prototypes && proto_scratch && out, CSS_E_ARG, "css_sim_map: null pointer");
     return css_rep_pass(rep, rep_dtype, prototypes, proto_scratch, B, C, D, h, w, mode, temp, out, nullptr, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// css_rows_refresh: "are these pixel-major rows still the rows of THIS map?"  The student pass hands rows / norms to the loss
+// on the `prob` tensor; the reference wraps the model in DistributedDataParallel(find_unused_parameters=True)
+// (mix_label.py:77), whose output sink CLONES rep_all, so the loss sees equal content at another address.  Instead of
+// re-reading the whole map (the rows-only pass), a sampled comparison decides on the device: thread p compares RV_SAMPLES
+// channels of pixel p (64 apart, offset rotating with p, so every channel plane and every pixel is touched) bit for bit with
+// the carried rows and raises meta[CSS_META_ROWS_STALE]; the rows-only pass that follows returns at once unless that word is
+// set.  No host synchronisation, graph-capturable.  The word is cleared by css_select, which therefore runs first.
+// ---------------------------------------------------------------------------------------------------------------
+#define RV_SAMPLES 4
+template <typename T>
+__global__ void __launch_bounds__(256) rows_verify_kernel(const T* __restrict__ rep, const T* __restrict__ rows, int hw, int N,
+                                                          int32_t* __restrict__ meta) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= N) return;
+    const int b = p / hw, s = p - b * hw;
+    const int d0 = (int)(((unsigned)p * 37u) & (unsigned)(CSS_D / RV_SAMPLES - 1));
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < RV_SAMPLES; ++i) {
+        const int d = d0 + i * (CSS_D / RV_SAMPLES);
+        const T a = rep[((size_t)b * CSS_D + d) * hw + s];
+        const T r = rows[(size_t)p * CSS_D + d];
+        if constexpr (sizeof(T) == 4) bad |= __float_as_uint(a) != __float_as_uint(r);
+        else bad |= __bfloat16_as_ushort(a) != __bfloat16_as_ushort(r);
+    }
+    if (bad) meta[CSS_META_ROWS_STALE] = 1;
+}
+
+extern "C" int css_rows_refresh(const void* rep, int rep_dtype, void* rows, float* norms, int32_t* meta, int B, int D, int h, int w,
+                                void* stream) {
+    CSS_CHECK_ARG(rep && rows && norms && meta, CSS_E_ARG, "css_rows_refresh: null pointer");
+    CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_rows_refresh: non-positive size");
+    CSS_CHECK_ARG(D == CSS_D, CSS_E_DIM, "css_rows_refresh: D must be %d", CSS_D);
+    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32 || rep_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_rows_refresh: rep dtype %d not supported",
+                  rep_dtype);
+    CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_rows_refresh: too many pixels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = h * w, N = B * hw;
+    const int32_t* guard = meta + CSS_META_ROWS_STALE;
+    if (rep_dtype == CSS_DTYPE_F32) {
+        rows_verify_kernel<float><<<(N + 255) / 256, 256, 0, st>>>((const float*)rep, (const float*)rows, hw, N, meta);
+        launch_rep_pass<0, true, float>((const float*)rep, nullptr, hw, N, 1, CSS_SIM_COS, 1.f, nullptr, (float*)rows, norms, st, guard);
+    } else {
+        rows_verify_kernel<__nv_bfloat16><<<(N + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)rep, (const __nv_bfloat16*)rows, hw, N, meta);
+        launch_rep_pass<0, true, __nv_bfloat16>((const __nv_bfloat16*)rep, nullptr, hw, N, 1, CSS_SIM_COS, 1.f, nullptr,
+                                                (__nv_bfloat16*)rows, norms, st, guard);
+    }
+    CSS_CHECK_LAUNCH("css_rows_refresh", 2);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

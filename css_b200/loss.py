@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .ops import _cuda_f32, rep_rows, rows_key
+from .ops import _cuda_f32, rep_rows
 
 
 class _Workspace:
@@ -69,20 +69,24 @@ class _ContrastFn(torch.autograd.Function):
         check(lib.css_select(ptr(label), ptr(mask), ptr(prob), float(mod.strong_threshold), B2, C, h, w, ptr(ws.valid_bits),
                              ptr(ws.hard_bits), ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), st),
               "css_select")
-        if cache is not None and cache.key == rows_key(rep):      # rows written by the same read that produced `prob`
-            rows, norms = cache.rows, cache.norms
-        else:
+        how = cache.match(rep) if cache is not None else "miss"
+        if how == "miss":
             rows, norms = rep_rows(rep)
+        else:                                   # rows written by the same read that produced `prob`
+            rows, norms = cache.rows, cache.norms
         rows_dt = _lib.DTYPE_BF16 if rows.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        if how == "verify":                     # equal content at another address (DDP's output clone): checked on the device
+            check(lib.css_rows_refresh(ptr(rep), rows_dt, ptr(rows), ptr(norms), ptr(ws.meta), B2, D, h, w, st), "css_rows_refresh")
+            cache.rebind(rep)
         check(lib.css_class_stats(ptr(rows), rows_dt, ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
                                   ptr(ws.class_stats), st), "css_class_stats")
         mod._exchange(ws.class_stats, C, D, dev)
+        # sync_prototypes (extension): every rank applies the SAME update to every globally present class from the summed
+        # statistics, so equal prototypes stay equal without a broadcast; default = the reference's rank-local rule
+        rule = _lib.UPDATE_GLOBAL if mod.sync_prototypes else _lib.UPDATE_LOCAL
         check(lib.css_proto_ema(ptr(prototypes), ptr(ws.class_stats), ptr(ws.meta), float(mod.alpha), float(1 - mod.alpha),
-                                float(mod.temp), C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
+                                float(mod.temp), rule, C, D, ptr(ws.proto_hat), ptr(ws.class_cdf), st), "css_proto_ema")
         torch.autograd.graph.increment_version(prototypes)     # updated in place through the raw pointer: tell autograd
-        if mod.sync_prototypes and dist.is_initialized() and dist.get_world_size(mod.process_group) > 1:
-            dist.broadcast(prototypes, src=dist.get_global_rank(mod.process_group, 0) if mod.process_group else 0,
-                           group=mod.process_group)
         anchor_px = torch.empty(C * Q, device=dev, dtype=torch.int32)
         grad_anchor = torch.empty(C * Q * D, device=dev, dtype=torch.float32) if want_grad else None
         loss = torch.empty((), device=dev, dtype=torch.float32)
@@ -104,7 +108,7 @@ class _ContrastFn(torch.autograd.Function):
         ctx.n_anchor = C * Q
         ctx.save_for_backward(anchor_px, grad_anchor)
         mod.last = dict(ws=ws, anchor_px=anchor_px, grad_anchor=grad_anchor, seed=seed, offset=offset, rows=rows, norms=norms,
-                        rows_from_cache=cache is not None and cache.key == rows_key(rep))
+                        rows_from_cache=how != "miss", rows_cache_mode=how)
         return loss
 
     @staticmethod
@@ -137,7 +141,8 @@ class Contrast_Loss(nn.Module):
         self.strong_threshold = strong_threshold
         self.alpha = alpha
         self.process_group = process_group
-        self.sync_prototypes = sync_prototypes   # extension, default off: the reference lets per-rank prototypes drift
+        # extension, default off (the reference lets per-rank prototypes drift): update every globally present class on every rank
+        self.sync_prototypes = sync_prototypes
         # how the [C, D+1] class statistics are summed over ranks: "peer" = css_stats_allreduce over NVLink peer memory
         # (one node), "nccl" = dist.all_reduce, "auto" = peer when every rank can map every other rank's buffer, else nccl
         self.exchange = exchange or os.environ.get("CSS_B200_EXCHANGE", "auto")
@@ -147,7 +152,7 @@ class Contrast_Loss(nn.Module):
         self._seed = seed
         self._step = 0
         self._counter = None
-        self._ws = None
+        self._ws = {}                         # one workspace per problem shape, never freed: a captured graph may still write to it
         self.last = None
         self.score_events = None              # set to a list to collect (start, end) CUDA events around css_score_ce
 
@@ -160,6 +165,9 @@ class Contrast_Loss(nn.Module):
         """Device-resident step counter of the Philox stream: the kernels read it as the draw offset and bump it, so the
         sampler advances without any host involvement (eager calls and CUDA-graph replays alike)."""
         if self._counter is None or self._counter.device != device:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("css_b200: the first Contrast_Loss.forward must run outside CUDA-graph capture (it creates the "
+                                   "device-resident sampler counter a captured graph then advances on every replay)")
             self._counter = torch.full((1,), self._step, device=device, dtype=torch.int64)
         return self._counter
 
@@ -197,9 +205,16 @@ class Contrast_Loss(nn.Module):
 
     def _workspace(self, B2, C, D, h, w, device):
         key = (B2, C, D, h, w, self.num_queries, self.num_negatives, str(device))
-        if self._ws is None or self._ws.key != key:
-            self._ws = _Workspace(B2, C, D, h, w, self.num_queries, self.num_negatives, device)
-        return self._ws
+        ws = self._ws.get(key)
+        if ws is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("css_b200: run one eager Contrast_Loss.forward of this shape before capturing it in a CUDA graph")
+            ws = self._ws[key] = _Workspace(B2, C, D, h, w, self.num_queries, self.num_negatives, device)
+        return ws
+
+    def clear_workspaces(self):
+        """Drops the per-shape scratch buffers (only when no captured CUDA graph refers to them any more)."""
+        self._ws = {}
 
     def forward(self, rep, label, mask, prob, prototypes, _indices=None):
         """rep [B2,256,h,w], label [B2,C,h,w], mask [B2,1,h,w], prob [B2,C,h,w], prototypes [C,256] (updated in place).

@@ -4,6 +4,8 @@ torch's caching allocator and call the C ABI (include/css_b200.h) on the current
 Every op raises on non-CUDA tensors: there is no CPU fallback (the CPU restatement lives in oracle/ and is test
 infrastructure only).  Reference lines are relative to the reference root (WangChangqi98/CSS).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -50,15 +52,38 @@ def proto_softmax_sim(rep_all, prototypes, temp, with_rows=True):
 
 
 class RowsCache:
-    """Pixel-major copy of one representation map, tagged with what it was derived from."""
+    """Pixel-major copy of one representation map, riding on the `prob` tensor it was produced with.
+
+    match(rep) decides how the loss may use it:
+      "same"   -- `rep` is the very tensor the rows were read from (same storage address, same version counter).  The cache
+                  keeps a detached alias of that tensor alive, so the caching allocator cannot hand its address to another
+                  tensor while the cache exists;
+      "verify" -- `rep` is another tensor of the same shape that was never modified in place (version 0), e.g. the clone
+                  DistributedDataParallel(find_unused_parameters=True) makes of every output that requires grad
+                  (mix_label.py:76-77).  The rows are then checked against `rep` ON THE DEVICE (css_rows_refresh: sampled
+                  bit-for-bit comparison, and a rows-only pass that runs only if it failed) -- no host synchronisation;
+      "miss"   -- anything else: the loss reads `rep` again.
+    CSS_B200_ROWS_CACHE=strict disables "verify" (identity only)."""
 
     def __init__(self, rep, rows, norms):
-        self.key = rows_key(rep)
+        self.src = rep.detach()
+        self.version = rep._version
         self.rows, self.norms = rows, norms
 
+    def match(self, rep):
+        src = self.src
+        if rep.shape != src.shape or rep.dtype != src.dtype or rep.device != src.device or not rep.is_contiguous():
+            return "miss"
+        if rep.data_ptr() == src.data_ptr() and rep._version == self.version and src._version == self.version:
+            return "same"
+        if rep._version == 0 and os.environ.get("CSS_B200_ROWS_CACHE", "verify") != "strict":
+            return "verify"
+        return "miss"
 
-def rows_key(rep):
-    return (rep.data_ptr(), tuple(rep.shape), rep._version, str(rep.device))
+    def rebind(self, rep):
+        """After css_rows_refresh the rows are those of `rep` (verified equal, or rewritten from it)."""
+        self.src = rep.detach()
+        self.version = rep._version
 
 
 def rep_rows(rep):
@@ -69,9 +94,25 @@ def rep_rows(rep):
     norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
-        check(lib.css_rep_pass(ptr(rep), dt, None, None, B, 1, D, h, w, _lib.SIM_COS, 1.0, None, ptr(rows), ptr(norms),
-                               stream_ptr()), "css_rep_pass")
+        _timed_rep_pass("rows_only",
+                        lambda: check(lib.css_rep_pass(ptr(rep), dt, None, None, B, 1, D, h, w, _lib.SIM_COS, 1.0, None, ptr(rows), ptr(norms),
+                                                       stream_ptr()), "css_rep_pass"))
     return rows, norms
+
+
+# set to a list to collect (start, end, label) CUDA events around every css_rep_pass launch (bench.py's live kernel timing)
+rep_pass_events = None
+
+
+def _timed_rep_pass(label, launch):
+    ev = rep_pass_events
+    if ev is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    ev.append((e0, e1, label))
 
 
 def _sim(rep, prototypes, mode, temp, with_rows=False):
@@ -89,8 +130,9 @@ def _sim(rep, prototypes, mode, temp, with_rows=False):
         norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(rep.device):
-        check(lib.css_rep_pass(ptr(rep), dt, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
-                               ptr(rows), ptr(norms), stream_ptr()), "css_rep_pass")
+        _timed_rep_pass("student" if with_rows else "teacher",
+                        lambda: check(lib.css_rep_pass(ptr(rep), dt, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp, ptr(out),
+                                                       ptr(rows), ptr(norms), stream_ptr()), "css_rep_pass"))
     if with_rows:
         out._css_rows = RowsCache(rep, rows, norms)
     return out

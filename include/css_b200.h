@@ -8,8 +8,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`; tensors are contiguous, NCHW;
- *   - the caller owns every buffer (inputs, outputs, scratch); the library never allocates or frees
- *     device memory and keeps no global device state;
+ *   - the caller owns every buffer (inputs, outputs, scratch); no data-path entry point allocates or frees
+ *     device memory or keeps global device state.  ONE documented exception, set-up only: css_comm_alloc /
+ *     css_comm_free own the small (<= 0.6 MB) peer-memory exchange buffer, because memory that is exported with a
+ *     CUDA IPC handle must be its own cudaMalloc allocation (a sub-block of a caching allocator's segment cannot be);
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
  *     synchronisation, and is CUDA-graph capturable;
  *   - return value: 0 = ok, <0 = argument error (see CSS_E_*), >0 = cudaError_t of the failed launch;
@@ -56,6 +58,7 @@ extern "C" {
 #define CSS_META_SLOT_OF_CLS  128    /* [32] slot of a class, -1 when absent                      */
 #define CSS_META_TICKET       160    /* internal: last-CTA election of the scan kernel            */
 #define CSS_META_DRAW_OFFSET  162    /* [2] lo/hi words of the Philox offset used by the last css_score_ce */
+#define CSS_META_ROWS_STALE   164    /* cleared by css_select, raised by css_rows_refresh when the carried rows differ */
 
 int         css_version(void);
 const char* css_last_error(void);
@@ -81,6 +84,18 @@ int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float*
                  float* sim_out, void* rows, float* norms, void* stream);
 int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                 int B, int C, int D, int h, int w, int mode, float temp, float* out, void* stream);
+
+/* ---- carried rows: "are these still the rows of THIS map?" ---------------------------------------------------------------
+ * The reference wraps the model in DistributedDataParallel(find_unused_parameters=True) (mix_label.py:76-77,
+ * cross_label.py, ori_pseudo.py alike); DDP's output sink clones rep_all, so the loss (loss.py:75) receives equal content at
+ * a different address than the map the student pass read.  css_rows_refresh keeps the one-read property without trusting
+ * addresses: a sampled bit-for-bit comparison of `rep` with `rows` (4 channels of every pixel, 64 apart, rotating with the
+ * pixel id) raises meta[CSS_META_ROWS_STALE] on any difference, and the rows-only pass that follows in the same call
+ * rewrites rows / norms from `rep` only if that word is set (otherwise it returns at once).  Call after css_select of the same
+ * step (which clears the word).  Two launches, no host synchronisation, graph-capturable.
+ */
+int css_rows_refresh(const void* rep, int rep_dtype, void* rows, float* norms, int32_t* meta,
+                     int B, int D, int h, int w, void* stream);
 
 /* ---- stage 1 / 1' / 2 ----------------------------------------------------------------------------------------
  * Fused bilinear (align_corners=True) up-sampling + softmax + max of the similarity map and of the class logits,
@@ -129,9 +144,16 @@ int css_class_stats(const void* rows, int rows_dtype, const uint32_t* valid_bits
  *   class_cdf f32[32*32] row k: inclusive CDF of softmax(cos(P_k, P_j)/temp) over the other present classes in the
  *                        rotated order k+1..V-1,0..k-1 (loss.py:133-135)
  *   class_stats is the (all-reduced) [C, D+1] block; meta supplies the LOCAL counts.
+ *   update_rule: CSS_UPDATE_LOCAL  = the reference's rule: a rank touches prototypes[c] only if c is present in ITS batch
+ *                                    (loss.py:96-97), so per-rank prototypes may drift apart exactly as in the reference;
+ *                CSS_UPDATE_GLOBAL = extension: every class with a positive GLOBAL count is updated on every rank -- ranks that
+ *                                    start from equal prototypes stay bit-identical, no broadcast needed.
  */
+#define CSS_UPDATE_LOCAL  0
+#define CSS_UPDATE_GLOBAL 1
 int css_proto_ema(float* prototypes, const float* class_stats, const int32_t* meta, float alpha,
-                  float one_minus_alpha, float temp, int C, int D, float* proto_hat, float* class_cdf, void* stream);
+                  float one_minus_alpha, float temp, int update_rule, int C, int D, float* proto_hat, float* class_cdf,
+                  void* stream);
 
 /* ---- stage 3: sampling (materialised; the scoring kernel can also draw on the fly) ---------------------------------
  * Anchors: Q uniform indices into each present class's hard list (loss.py:127).  Negatives: Nn iid draws of
@@ -229,9 +251,17 @@ int css_cut_mix(const float* image, const int64_t* label_a, const int64_t* label
  *   css_comm_open   : map a peer's buffer from its handle; css_comm_close unmaps it; css_comm_free releases the own buffer
  *   css_stats_allreduce: class_stats (device, in place) <- sum over ranks.  peer_buffers: DEVICE array of `world` device
  *                     pointers, entry r = rank r's buffer as mapped in this process (entry `rank` = local_buffer).  One launch,
- *                     no host synchronisation, CUDA-graph capturable; every rank must make the same sequence of calls.  A peer
- *                     that does not arrive within 2 s turns the result into NaN instead of hanging the GPU.
+ *                     no host synchronisation, CUDA-graph capturable; every rank must make the same sequence of calls.
+ *   A peer that does not arrive within the timeout (css_comm_set_timeout_ms, process-wide, default 600 000 ms like the NCCL
+ *   watchdog) does not hang the GPU and does not poison anything: class_stats is left as this rank's LOCAL statistics and the
+ *   event is counted; css_comm_timeouts(buffer) returns that count from pinned host memory without synchronising, so the
+ *   caller can poll it every step and raise.
  */
+int css_comm_set_timeout_ms(unsigned long long ms);
+int css_comm_timeouts(void* buffer);
+/* diagnostics (blocking device read, never inside a timed region): out3_host = {completed calls, timeouts, total nanoseconds
+ * the calls spent waiting for the slowest peer's block} */
+int css_comm_stats(void* buffer, unsigned long long* out3_host);
 size_t css_comm_bytes(int world);
 int css_comm_alloc(int world, void** buffer);
 int css_comm_free(void* buffer);

@@ -1,9 +1,12 @@
-"""Harness that imports the UNMODIFIED reference (WangChangqi98/CSS) from /root/reference.
+"""Harness that imports the UNMODIFIED reference (WangChangqi98/CSS).
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py in the build container to run
-the live reference on CPU and record its outputs + RNG draws as golden fixtures.  It
-never runs on the GPU box (``/root/reference`` does not exist there) and nothing in
-``css_b200/`` imports it.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py in the build container to run
+the live reference on CPU and record its outputs + RNG draws as golden fixtures, and by
+oracle/ref_bench.py for bench.py's reference timings.  Nothing in ``css_b200/`` imports it.
+
+Where the reference is looked for: $CSS_REFERENCE_ROOT, then ``baseline/_ref`` (a git-ignored copy
+of the reference's Python tree that ``__graft_entry__.build()`` makes where /root/reference exists;
+it travels to the GPU box with the snapshot), then /root/reference.
 
 Shims (none of them edits the reference):
   1. single-process gloo group  -- ``concat_all_gather`` is unconditional
@@ -19,28 +22,50 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-REF_ROOT = os.environ.get("CSS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("CSS_REFERENCE_ROOT"), os.path.join(os.path.dirname(_HERE), "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "generalframeworks")):
+            return cand
+    return os.environ.get("CSS_REFERENCE_ROOT", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
     return os.path.isdir(os.path.join(REF_ROOT, "generalframeworks"))
 
 
+@contextlib.contextmanager
+def cpu_cuda_shim():
+    """Shim (2) as a scope: while the reference runs on CPU tensors on a box that HAS a GPU, loss.py:147's `.cuda()` must stay
+    a no-op, and must be the real thing again afterwards."""
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
+
+
 _mods = {}
 
 
-def load_reference():
+def load_reference(device="cpu"):
     """Returns (loss_module, ddp_model_module, utils_module) of the reference."""
+    if not dist.is_initialized():                  # concat_all_gather is unconditional: a world-1 group for CPU and CUDA tensors
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29571")
+        dist.init_process_group("cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo", rank=0, world_size=1)
     if _mods:
         return _mods["L"], _mods["M"], _mods["U"]
     if not reference_available():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
-    if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29571")
-        dist.init_process_group("gloo", rank=0, world_size=1)
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
     import generalframeworks.loss.loss as L

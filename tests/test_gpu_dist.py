@@ -147,3 +147,89 @@ def test_generate_cut_gather_world2_uses_rank0_partners():
     out = mgr.dict()
     mp.spawn(_cutmix_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _timeout_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["CSS_B200_COMM_TIMEOUT_S"] = "0.4" if rank == 0 else "600"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    import time
+    from css_b200.comm import PeerStatsReducer
+    C, D = 21, 256
+    red = PeerStatsReducer("cuda:0")
+    res = dict(ok=red.ok)
+    if red.ok:
+        mine = torch.full((C, D + 1), float(rank + 1)).cuda()
+        x = mine.clone()
+        if rank == 1:
+            time.sleep(2.5)                          # a late rank (checkpoint write, loader respawn, ...)
+        red.allreduce(x, C, D)
+        torch.cuda.synchronize()
+        res["timeouts"] = red.timeouts()
+        res["finite"] = bool(torch.isfinite(x).all().item())
+        if rank == 0:                                # gave up after 0.4 s: statistics stay LOCAL (never NaN), the event is counted,
+            res["kept_local"] = bool(torch.equal(x, mine))      # and the next call raises instead of training on
+            try:
+                red.allreduce(x, C, D)
+                res["raised"] = False
+            except RuntimeError as e:
+                res["raised"] = "timed out" in str(e)
+        else:                                        # the late rank finds rank 0's block waiting for it: full sum
+            res["summed"] = bool(torch.equal(x, torch.full((C, D + 1), 3.0).cuda()))
+        dist.barrier()
+        red.close()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_timeout_is_counted_not_poisoned():
+    """a rank that is late by more than the timeout must not turn the prototypes into NaN silently."""
+    port = 29600 + (os.getpid() % 90)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_timeout_worker, args=(2, port, out), nprocs=2, join=True)
+    if not out[0]["ok"]:
+        pytest.skip("CUDA IPC between the two test processes is not available on this box")
+    assert out[0]["timeouts"] == 1 and out[0]["kept_local"] and out[0]["finite"] and out[0]["raised"], dict(out[0])
+    assert out[1]["timeouts"] == 0 and out[1]["summed"], dict(out[1])
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    import css_b200
+    g = load_golden("loss_mix_c21")
+    Q, Nn = int(g["Q"]), int(g["Nn"])
+    sl = slice(rank, rank + 1)
+    res = {}
+    for sync in (False, True):
+        crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=float(g["temp"]), strong_threshold=float(g["strong"]),
+                                      alpha=float(g["alpha"]), seed=7 + rank, sync_prototypes=sync).cuda()
+        protos = torch.from_numpy(g["s0_proto_in"].copy()).cuda()
+        for _ in range(2):
+            with torch.no_grad():
+                crit(torch.from_numpy(g["s0_rep"][sl].copy()).cuda(), torch.from_numpy(g["s0_label"][sl].astype(np.float32)).cuda(),
+                     torch.from_numpy(g["s0_mask"][sl].astype(np.float32)).cuda(), torch.from_numpy(g["s0_prob"][sl].copy()).cuda(), protos)
+        res[sync] = protos.cpu().numpy()
+        res[("present", sync)] = crit.selection()["present"]
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_sync_prototypes_keeps_ranks_bit_identical():
+    """sync_prototypes=True updates every globally present class on every rank from the summed statistics
+    (no broadcast after the fact), so equal prototypes stay equal; the default keeps the reference's rank-local rule."""
+    port = 29500 + (os.getpid() % 90)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sync_worker, args=(2, port, out), nprocs=2, join=True)
+    assert np.array_equal(out[0][True], out[1][True])
+    if out[0][("present", False)] != out[1][("present", False)]:        # different local class sets: the reference rule drifts
+        assert not np.array_equal(out[0][False], out[1][False])
+    # classes present on both ranks get the same update under either rule
+    both = sorted(set(out[0][("present", False)]) & set(out[1][("present", False)]))
+    assert both and np.array_equal(out[0][False][both], out[0][True][both])

@@ -243,10 +243,16 @@ def test_full_size_properties_voc_batch():
     protos3 = torch.zeros(C, 256).cuda()
     assert crit3(d["rep"].cuda(), label, mask, prob, protos3).item() == loss.item()
     assert torch.equal(protos3, protos)
-    # EMA branch on a second step: p <- alpha p + (1-alpha) mean
+    # EMA branch on a second step with a DIFFERENT batch: p <- alpha p + (1-alpha) mean(second batch) (loss.py:102,108)
     before = protos.clone()
-    crit(d["rep"].cuda(), label, mask, prob, protos)
-    torch.testing.assert_close(protos, 0.99 * before + (1 - 0.99) * before, rtol=1e-5, atol=1e-6)
+    d2 = synth.student_batch(B2, C, h, w, seed=99)
+    crit(d2["rep"].cuda(), d2["label"].cuda(), d2["mask"].cuda(), d2["prob"].cuda(), protos)
+    x2 = d2["rep"].permute(0, 2, 3, 1).reshape(-1, 256).double()
+    valid2 = ((d2["label"] * d2["mask"]) != 0).permute(0, 2, 3, 1).reshape(-1, C)
+    assert not torch.equal(before, protos)
+    for c in range(C):
+        want = 0.99 * before[c].double().cpu() + 0.01 * x2[valid2[:, c]].mean(0) if valid2[:, c].any() else before[c].double().cpu()
+        np.testing.assert_allclose(protos[c].cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
 
 
 def test_model_shells_with_stub_network():

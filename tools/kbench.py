@@ -82,7 +82,7 @@ def main():
     p2 = protos.clone()
 
     def ema(i):
-        check(lib.css_proto_ema(ptr(p2), ptr(ws.class_stats), ptr(ws.meta), 0.99, 0.01, temp, C, D, ptr(ws.proto_hat),
+        check(lib.css_proto_ema(ptr(p2), ptr(ws.class_stats), ptr(ws.meta), 0.99, 0.01, temp, 0, C, D, ptr(ws.proto_hat),
                                 ptr(ws.class_cdf), stream_ptr()), "ema")
 
     anchor_px = torch.empty(C * Q, device=dev, dtype=torch.int32)
