@@ -315,7 +315,7 @@ def reference_arm(args, cfg):
         "e2e": {"value": r["value"], "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -329,9 +329,50 @@ def workload_config(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything written to fd 1 from here on (NCCL's version banner, library chatter) goes to stderr; the JSON line is
+    written to the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def time_in_graph(fn, iters=20, warm=3):
+    """Average device time (ms) of one call of `fn`: `iters` calls captured into ONE CUDA graph and replayed between two CUDA
+    events on the launching stream (no host launch gaps inside the number)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def main():
     args = parse()
     cfg = WORKLOADS[args.workload]
+    quiet_stdout()
     if args.impl == "reference":
         return reference_arm(args, cfg)
 
@@ -449,7 +490,6 @@ def main():
     # ---- timed region: device-resident inputs ------------------------------------------------------------------------
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    crit.score_events = [] if graph is None else None
     launches_per_step = None
     if graph is not None:      # launches inside a replayed graph are not re-counted by the library: count one eager step
         l0 = lib.css_launch_count()
@@ -470,18 +510,30 @@ def main():
     comm1 = reducer.stats() if comm0 is not None else None
     launches = lib.css_launch_count() - launches0 if graph is None else launches_per_step * args.steps
     clocks = sampler.stop()
-    # live CUDA-event timing of the kernels the roofline reports, on the launching stream, eager launches of the same steps
-    crit.score_events = []
-    css_b200.ops.rep_pass_events = []
-    for _ in range(min(args.steps, 50)):
-        step(gpu)
-    barrier()
-    score_ms = [a.elapsed_time(b) for a, b in crit.score_events]
+    # live CUDA-event timing of the kernels the rooflines report: each op alone, 20 launches captured in one CUDA graph and
+    # replayed between two events on the launching stream (eager launches would add host launch gaps to a 70 us kernel)
+    last = crit.last
+    ws_, rows_, norms_ = last["ws"], last["rows"], last["norms"]
+    rows_dt_ = _lib.DTYPE_BF16 if rows_.dtype == torch.bfloat16 else _lib.DTYPE_F32
+    ga_ = torch.empty(C * Q * D, device=dev, dtype=torch.float32)
+    apx_ = torch.empty(C * Q, device=dev, dtype=torch.int32)
+    loss_ = torch.empty((), device=dev, dtype=torch.float32)
+    cnt_ = torch.zeros(1, device=dev, dtype=torch.int64)
+
+    def score_once():
+        _lib.check(lib.css_score_ce(_lib.ptr(rows_), rows_dt_, _lib.ptr(norms_), _lib.ptr(ws_.proto_hat), _lib.ptr(ws_.class_cdf),
+                                    _lib.ptr(ws_.valid_list), _lib.ptr(ws_.hard_list), _lib.ptr(ws_.meta), None, None, 3407, 0,
+                                    _lib.ptr(cnt_), N, C, D, Q, Nn, float(temp), _lib.ptr(ws_.loss_kq), _lib.ptr(apx_), _lib.ptr(ga_),
+                                    _lib.ptr(loss_), _lib.stream_ptr()), "css_score_ce")
+
+    score_avg_ms = time_in_graph(score_once)
     rep_ms = {}
-    for a, b, label in css_b200.ops.rep_pass_events:
-        rep_ms.setdefault(label, []).append(a.elapsed_time(b))
-    crit.score_events = None
-    css_b200.ops.rep_pass_events = None
+    if strategy != "ori":
+        rep_ms["student"] = time_in_graph(lambda: css_b200.ops.proto_softmax_sim(gpu["rep_all"], protos, temp))
+        rep_ms["teacher"] = time_in_graph(lambda: css_b200.ops.cos_sim_map(gpu["rep_u"], protos))
+    else:
+        rep_ms["rows_only"] = time_in_graph(lambda: css_b200.ops.rep_rows(gpu["rep_all"]))
+    barrier()
     t_all = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
     t_mine = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -624,7 +676,6 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     stream_b, gather_b = path_bytes(cfg, v_eff)
-    score_avg_ms = sum(score_ms) / max(len(score_ms), 1)
     achieved = gather_b / (score_avg_ms * 1e-3) / 1e9 if score_avg_ms > 0 else 0.0
     prof = {}
     prof_path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
@@ -661,17 +712,17 @@ def main():
     # the HBM-bound streaming kernel: the student rep pass (one read of rep_all -> prob_all + pixel-major rows + norms)
     roofline_hbm = None
     if rep_ms.get("student"):
-        t_st = sum(rep_ms["student"]) / len(rep_ms["student"])
+        t_st = rep_ms["student"]
         s_el = 4
         alg = N * (D * s_el + 4 * C + D * s_el + 4)
         tr = prof.get("rep_pass_student")
-        roofline_hbm = {"bound": "hbm", "kernel": "rep_pass_kernel<SOFTMAX, rows> (css_rep_pass, student; the timing includes the "
-                        "2 us prototype-preparation launch of the same call)", "achieved": alg / (t_st * 1e-3) / 1e9, "peak": peak,
+        roofline_hbm = {"bound": "hbm", "kernel": "rep_pass_kernel<SOFTMAX, rows> (css_rep_pass, student: one read of rep_all -> prob_all + pixel-major "
+                        "rows + norms; timed with the prototype-preparation launch of the same call)", "achieved": alg / (t_st * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg / (t_st * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": tr,
                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_st, "share_of_step": t_st / ms_per_step,
                         "dram_frac_of_hbm": (tr / (t_st * 1e-3) / 1e9 / peak) if tr else None,
                         "copy_gbs_live": probe.get("copy_gbs") if probe else None,
-                        "teacher_avg_launch_ms": (sum(rep_ms["teacher"]) / len(rep_ms["teacher"])) if rep_ms.get("teacher") else None}
+                        "teacher_avg_launch_ms": rep_ms.get("teacher")}
 
     cpu = None
     gpu_eager = None
@@ -703,7 +754,9 @@ def main():
             "exchange_check": exchange_check, "multi_gpu": multi, "ddp_clone_step": ddp_line,
             "clocks": clocks, "loss": loss_value, "present_classes": V, "scored_classes": v_eff,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
+    if world == 1 and dist.is_initialized():
+        dist.destroy_process_group()
     if world > 1:
         # graphs that captured NCCL work must be released before the communicator goes away; then leave without the
         # interpreter's atexit teardown, which can deadlock on a communicator that was used inside a captured graph
