@@ -1,7 +1,14 @@
 // Stage 1 / 1b / 1' / 2: similarity maps against the class prototypes, fused up-sample + softmax + max + fusion.
 // Reference: generalframeworks/networks/ddp_model.py:104-118, 147-154 (Model_mix); :189-199, 230-237 (Model_cross);
 // :36-37 (Model_ori_pseudo).
+#include <stdlib.h>
+
 #include "css_common.cuh"
+
+#define CSS_REP_PASS_DEFAULT_TC 0
+int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scratch, int B, int C, int h, int w, int mode, float temp,
+                    float* sim_out, float* rows, float* norms, cudaStream_t st);
+bool css_rep_pass_use_tc();
 
 // ---------------------------------------------------------------------------------------------------------------
 // prototype preparation: F.normalize(prototypes, dim=-1) (eps 1e-12, ddp_model.py:107), transposed to [D][32]
@@ -255,6 +262,23 @@ static void dispatch_rep_pass(int ng, const T* rep, const float* scratch, int hw
     }
 }
 
+// which multiply side css_rep_pass uses for fp32 maps: the tcgen05 / TMEM kernel of css_sim_tc.cu ("tc") or the FFMA2 kernel
+// above ("fma"); CSS_B200_REP_PASS overrides the default, css_set_rep_pass_path() overrides both (tests time and compare the two)
+static int g_rep_pass_tc = -1;
+extern "C" int css_set_rep_pass_path(int use_tc) {
+    g_rep_pass_tc = use_tc < 0 ? -1 : (use_tc ? 1 : 0);
+    return 0;
+}
+bool css_rep_pass_use_tc() {
+    if (g_rep_pass_tc >= 0) return g_rep_pass_tc != 0;
+    static int env = -1;
+    if (env < 0) {
+        const char* v = getenv("CSS_B200_REP_PASS");
+        env = (v && v[0] == 't') ? 1 : (v && v[0] == 'f') ? 0 : CSS_REP_PASS_DEFAULT_TC;
+    }
+    return env != 0;
+}
+
 extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C, int D, int h,
                             int w, int mode, float temp, float* sim_out, void* rows, float* norms, void* stream) {
     const bool want_sim = sim_out != nullptr, want_rows = rows != nullptr;
@@ -262,7 +286,7 @@ extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototy
     CSS_CHECK_ARG(!want_sim || (prototypes && proto_scratch), CSS_E_ARG, "css_rep_pass: sim_out needs prototypes and proto_scratch");
     CSS_CHECK_ARG(want_rows == (norms != nullptr), CSS_E_ARG, "css_rep_pass: rows and norms go together");
     CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_rep_pass: non-positive size");
-    CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX, CSS_E_ARG, "css_rep_pass: bad mode %d", mode);
+    CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX || (mode == 2 && css_rep_pass_use_tc()), CSS_E_ARG, "css_rep_pass: bad mode %d", mode);
     if (int e = css_check_dims(want_sim ? C : 1, D)) return e;
     CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32 || rep_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_rep_pass: rep dtype %d not supported",
                   rep_dtype);
@@ -270,6 +294,12 @@ extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototy
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w, N = B * hw;
     int launches = 1;
+    if (want_sim && rep_dtype == CSS_DTYPE_F32 && css_rep_pass_use_tc()) {       // tensor-core path (css_sim_tc.cu)
+        if (int e = css_rep_pass_tc((const float*)rep, prototypes, proto_scratch, B, C, h, w, mode, temp, sim_out, (float*)rows, norms, st))
+            return e;
+        CSS_CHECK_LAUNCH("css_rep_pass", 2);
+        return 0;
+    }
     if (want_sim) {
         proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
         ++launches;

@@ -32,7 +32,7 @@ def _cuda_rep(t, name="rep"):
 
 
 def _proto_scratch(device):
-    return torch.empty(_lib.D * _lib.CMAX, device=device, dtype=torch.float32)
+    return torch.empty(2 * _lib.D * _lib.CMAX, device=device, dtype=torch.float32)
 
 
 def cos_sim_map(rep, prototypes):

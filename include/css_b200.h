@@ -71,7 +71,7 @@ unsigned long long css_launch_count(void);
  * css_rep_pass produces any combination of
  *  (a) sim_out [B,C,h,w] f32: cosine (mode CSS_SIM_COS) or softmax_c(cos/temp) (CSS_SIM_SOFTMAX) similarity of every
  *      pixel's D-vector against the class prototypes.  Replaces ddp_model.py:104-110 (teacher sim_mat) and
- *      :147-154 / :230-237 (student prob_all).  Needs prototypes [C,D] and proto_scratch f32[D*32] (normalised,
+ *      :147-154 / :230-237 (student prob_all).  Needs prototypes [C,D] and proto_scratch f32[2*D*32] (normalised,
  *      transposed prototypes; F.normalize eps 1e-12).
  *  (b) rows [N*D] + norms f32[N]: the pixel-major copy (row p = pixel id p, raw values, SAME dtype as rep: a bf16 map gives
  *      lossless bf16 rows and halves the gather bytes) and ||x_p||, from which the loss gathers candidate rows and
@@ -84,6 +84,11 @@ int css_rep_pass(const void* rep, int rep_dtype, const float* prototypes, float*
                  float* sim_out, void* rows, float* norms, void* stream);
 int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* proto_scratch,
                 int B, int C, int D, int h, int w, int mode, float temp, float* out, void* stream);
+/* (a) has two implementations for fp32 maps: tcgen05.mma kind::tf32 with TMEM accumulators and an fp32-exact hi/lo operand split
+ * (css_sim_tc.cu), and packed-FFMA2 CUDA-core dots (css_sim.cu; always used for bf16 maps and for (b) alone).
+ * css_set_rep_pass_path(1 / 0) selects one for this process, -1 returns to the default / the CSS_B200_REP_PASS=tc|fma
+ * environment variable.  Both meet the path's tolerances (similarities abs 2e-6, labels identical away from 1e-5 near-ties). */
+int css_set_rep_pass_path(int use_tc);
 
 /* ---- carried rows: "are these still the rows of THIS map?" ---------------------------------------------------------------
  * The reference wraps the model in DistributedDataParallel(find_unused_parameters=True) (mix_label.py:76-77,
