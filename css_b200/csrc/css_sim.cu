@@ -442,59 +442,44 @@ __device__ __forceinline__ void upsample_softmax_max(const float* __restrict__ s
     label = lab;
 }
 
-// ---- staged path: a thread owns a COLUMN STRIP of K2S_SY vertically adjacent crop pixels --------------------------------------
-// Vertically adjacent crop pixels mostly share their two source rows (for 81 -> 321 and 193 -> 769 the scale is exactly 1/4:
-// four crop rows per source row), and the horizontal interpolation of a source row, hx*v(x0) + lx*v(x1), depends only on the
-// crop column.  So the strip computes `top` / `bot` (one horizontally interpolated value per class for rows y0 / y1) ONCE and
-// every pixel of the strip only adds the vertical step hy*top + ly*bot: per pixel and class ~1.5 packed ops and 1/4 of the
-// shared loads instead of 4.5 ops and 4 loads, with the very same IEEE operations in the same order as ATen (bit-identical).
-// When the source row advances inside a strip (general scales) the old `bot` becomes the new `top`.
-#define K2S_SY 4
-#define K2S_STRIPS 4
-#define K2S_TH (K2S_SY * K2S_STRIPS)
-#define K2S_TW 32
-
-__device__ __forceinline__ float max3f(float a, float b, float c) {
-    float r;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3 (sm_100)
-    return r;
-}
-
-// horizontally interpolated source row: out[c] = hx * row[x0][c] + lx * row[x1][c]   (tile is position-major [pos][CP])
-template <int CP>
-__device__ __forceinline__ void hlerp_row(const float* __restrict__ p0, const float* __restrict__ p1, float2 hx, float2 lx,
-                                          float2 (&out)[CP / 2]) {
-    const float4* a4 = reinterpret_cast<const float4*>(p0);
-    const float4* b4 = reinterpret_cast<const float4*>(p1);
-#pragma unroll
-    for (int g = 0; g < CP / 4; ++g) {
-        const float4 a = a4[g], b = b4[g];
-        out[2 * g + 0] = __fadd2_rn(__fmul2_rn(hx, make_float2(a.x, a.y)), __fmul2_rn(lx, make_float2(b.x, b.y)));
-        out[2 * g + 1] = __fadd2_rn(__fmul2_rn(hx, make_float2(a.z, a.w)), __fmul2_rn(lx, make_float2(b.z, b.w)));
-    }
-}
-
-// vertical step + softmax + max of one crop pixel from the strip's shared rows; same result as upsample_softmax_max
+// Same result as upsample_softmax_max, for the staged tile: position-major [pos][CP] (CP = C rounded up to 4), so one
+// 128-bit shared load per tap brings four classes and the interpolation runs on packed fp32 pairs (FMUL2 / FADD2: each
+// half is the same IEEE round-to-nearest op as the scalar form, so labels stay bit-exact).  ~12 issue slots per class
+// instead of ~32 (4 LDS + 4 address LEAs + 10 scalar flops + ...): the kernel is issue-bound, not HBM-bound.
 template <int CT>
-__device__ __forceinline__ void vlerp_softmax_max(const float2 (&top)[(CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX) / 2],
-                                                  const float2 (&bot)[(CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX) / 2], int C, float hyf, float lyf,
-                                                  int tmode, float temp, float rtemp, float& conf, int& label) {
+__device__ __forceinline__ void upsample_softmax_max_tile(const float* __restrict__ tile, int C, const Taps& t, int tmode, float temp,
+                                                          float rtemp, float& conf, int& label) {
     constexpr int CP = CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX;
-    const float2 hy = make_float2(hyf, hyf), ly = make_float2(lyf, lyf), rt = make_float2(rtemp, rtemp);
+    const float4* p00 = reinterpret_cast<const float4*>(tile + t.o00 * CP);
+    const float4* p01 = reinterpret_cast<const float4*>(tile + t.o01 * CP);
+    const float4* p10 = reinterpret_cast<const float4*>(tile + t.o10 * CP);
+    const float4* p11 = reinterpret_cast<const float4*>(tile + t.o11 * CP);
+    const float2 hx = make_float2(t.hx, t.hx), lx = make_float2(t.lx, t.lx);
+    const float2 hy = make_float2(t.hy, t.hy), ly = make_float2(t.ly, t.ly);
+    const float2 rt = make_float2(rtemp, rtemp);
     float2 v[CP / 2];
 #pragma unroll
-    for (int i = 0; i < CP / 2; ++i) {
-        float2 val = __fadd2_rn(__fmul2_rn(hy, top[i]), __fmul2_rn(ly, bot[i]));
-        if (tmode == 1) val = __fmul2_rn(val, rt);
-        else if (tmode == 2) val = make_float2(__fdiv_rn(val.x, temp), __fdiv_rn(val.y, temp));
-        v[i] = val;
+    for (int g = 0; g < CP / 4; ++g) {
+        const float4 a = p00[g], b = p01[g], c = p10[g], d = p11[g];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const float2 a2 = hh ? make_float2(a.z, a.w) : make_float2(a.x, a.y);
+            const float2 b2 = hh ? make_float2(b.z, b.w) : make_float2(b.x, b.y);
+            const float2 c2 = hh ? make_float2(c.z, c.w) : make_float2(c.x, c.y);
+            const float2 d2 = hh ? make_float2(d.z, d.w) : make_float2(d.x, d.y);
+            const float2 top = __fadd2_rn(__fmul2_rn(hx, a2), __fmul2_rn(lx, b2));
+            const float2 bot = __fadd2_rn(__fmul2_rn(hx, c2), __fmul2_rn(lx, d2));
+            float2 val = __fadd2_rn(__fmul2_rn(hy, top), __fmul2_rn(ly, bot));
+            if (tmode == 1) val = __fmul2_rn(val, rt);
+            else if (tmode == 2) val = make_float2(__fdiv_rn(val.x, temp), __fdiv_rn(val.y, temp));
+            v[2 * g + hh] = val;
+        }
     }
     float m = -INFINITY;
 #pragma unroll
     for (int i = 0; i < CP / 2; ++i) {
-        const bool okx = CT > 0 ? (2 * i < CT) : (2 * i < C), oky = CT > 0 ? (2 * i + 1 < CT) : (2 * i + 1 < C);
-        if (okx && oky) m = max3f(m, v[i].x, v[i].y);
-        else if (okx) m = fmaxf(m, v[i].x);
+        if (CT > 0 ? (2 * i < CT) : (2 * i < C)) m = fmaxf(m, v[i].x);
+        if (CT > 0 ? (2 * i + 1 < CT) : (2 * i + 1 < C)) m = fmaxf(m, v[i].y);
     }
     const float2 nm = make_float2(-m, -m), l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
     float sum = 0.f;
@@ -514,34 +499,37 @@ __device__ __forceinline__ void vlerp_softmax_max(const float2 (&top)[(CT > 0 ? 
     label = lab;
 }
 
-template <int CT>
-__global__ void __launch_bounds__(K2S_STRIPS * K2S_TW, 4) upsample_label_fuse_strip_kernel(
+template <bool STAGED, int CT>
+__global__ void __launch_bounds__(K2_TH * K2_TW, STAGED ? 5 : 1) upsample_label_fuse_kernel(
     const float* __restrict__ sim, const float* __restrict__ logits, float temp, float rtemp, int tmode, int fuse_mode, int C, int h, int w, int H, int W,
     float ry, float rx, int tile_cap, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
     int64_t* __restrict__ label_cls, float* __restrict__ fused) {
-    constexpr int CP = CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX;
-    extern __shared__ __align__(16) float tile[];   // [2 maps][tile_cap positions][CP classes]
+    extern __shared__ __align__(16) float tile[];   // [2 maps][tile_cap positions][CP classes]  (STAGED only)
     const int b = blockIdx.z;
-    const int Y0 = blockIdx.y * K2S_TH, X0 = blockIdx.x * K2S_TW;
+    const int Y0 = blockIdx.y * K2_TH, X0 = blockIdx.x * K2_TW;
+    const int Y = Y0 + (threadIdx.x >> 5), X = X0 + (threadIdx.x & 31);
     const int hw = h * w;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- stage the low-resolution footprint of this tile, position-major ----
-    const int Yl = min(Y0 + K2S_TH - 1, H - 1), Xl = min(X0 + K2S_TW - 1, W - 1);
-    const int ys0 = (int)__fmul_rn(ry, (float)Y0), xs0 = (int)__fmul_rn(rx, (float)X0);
-    const int ye = (int)__fmul_rn(ry, (float)Yl), xe = (int)__fmul_rn(rx, (float)Xl);
-    const int in_th = min(ye + 1, h - 1) - ys0 + 1;
-    const int in_tw = min(xe + 1, w - 1) - xs0 + 1;
-    const int npos = in_th * in_tw;                 // <= tile_cap by construction of the launch
-    {
-        // a warp walks 4-position x 8-class blocks: the global side reads 16-byte runs, the shared side lands in distinct banks
-        // for CP = 24; the only run-time division, r -> (yy, xx), is done in fp32 (exact: r < 2^12)
+    int ys0 = 0, xs0 = 0, in_tw = w, cstride = hw;
+    if (STAGED) {
+        const int Yl = min(Y0 + K2_TH - 1, H - 1), Xl = min(X0 + K2_TW - 1, W - 1);
+        ys0 = (int)__fmul_rn(ry, (float)Y0);
+        xs0 = (int)__fmul_rn(rx, (float)X0);
+        const int ye = (int)__fmul_rn(ry, (float)Yl), xe = (int)__fmul_rn(rx, (float)Xl);
+        const int in_th = min(ye + 1, h - 1) - ys0 + 1;
+        in_tw = min(xe + 1, w - 1) - xs0 + 1;
+        cstride = in_th * in_tw;                    // <= tile_cap by construction of the launch
+        // transpose NCHW -> [pos][CP] through a 4-position x 8-class lane pattern: the global side reads 16-byte runs,
+        // the shared side lands in 32 distinct banks for CP = 24 (stride 24 floats: rows 0,24,16,8 + 8 classes each)
+        constexpr int CP = CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX;
+        // a warp walks 4-position x 8-class blocks; the only run-time division, r -> (yy, xx), is done in fp32 (exact: r < 2^12)
         constexpr int CB = (CP + 7) >> 3;
-        const int RB = (npos + 3) >> 2;
+        const int RB = (cstride + 3) >> 2;
         const float inv_tw = __frcp_ru((float)in_tw);
-        for (int blk = wid; blk < RB * CB; blk += K2S_STRIPS) {
-            const int c_hi = blk % CB, r_hi = blk / CB;
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int blk = wid; blk < RB * CB; blk += K2_TH) {
+            const int c_hi = blk % CB, r_hi = blk / CB;              // CB is a compile-time constant
             const int r = r_hi * 4 + (lane & 3), c = c_hi * 8 + (lane >> 2);
-            if (r < npos && c < CP) {
+            if (r < cstride && c < CP) {
                 int yy = (int)(((float)r + 0.5f) * inv_tw);
                 yy -= (yy * in_tw > r);
                 const int xx = r - yy * in_tw;
@@ -552,85 +540,6 @@ __global__ void __launch_bounds__(K2S_STRIPS * K2S_TW, 4) upsample_label_fuse_st
         }
         __syncthreads();
     }
-    const int X = X0 + lane;
-    const int Ys = Y0 + wid * K2S_SY;
-    if (X >= W || Ys >= H) return;
-    // column taps (shared by the whole strip)
-    const float xs = __fmul_rn(rx, (float)X);
-    const int x0 = (int)xs, x1 = x0 + (x0 < w - 1);
-    const float lxf = __fsub_rn(xs, (float)x0), hxf = __fsub_rn(1.f, lxf);
-    const float2 hx = make_float2(hxf, hxf), lx = make_float2(lxf, lxf);
-    const int c0 = (x0 - xs0) * CP, c1 = (x1 - xs0) * CP;
-    // row taps of the strip's pixels
-    int y0s[K2S_SY];
-    float lys[K2S_SY], hys[K2S_SY];
-#pragma unroll
-    for (int i = 0; i < K2S_SY; ++i) {
-        const float ysf = __fmul_rn(ry, (float)min(Ys + i, H - 1));
-        y0s[i] = (int)ysf;
-        lys[i] = __fsub_rn(ysf, (float)y0s[i]);
-        hys[i] = __fsub_rn(1.f, lys[i]);
-    }
-    int lr[K2S_SY], lc[K2S_SY];
-#pragma unroll
-    for (int i = 0; i < K2S_SY; ++i) { lr[i] = -1; lc[i] = -2; }
-#pragma unroll
-    for (int map = 0; map < 2; ++map) {
-        const float* src = map == 0 ? sim : logits;
-        if (src == nullptr) continue;
-        const float* tm = tile + (size_t)map * tile_cap * CP;
-        float* conf_out = map == 0 ? conf_rep : conf_cls;
-        int64_t* label_out = map == 0 ? label_rep : label_cls;
-        const int tm_mode = map == 0 ? tmode : 0;
-        float2 top[CP / 2], bot[CP / 2];
-        int cur_y0 = -1, cur_y1 = -1;
-#pragma unroll
-        for (int i = 0; i < K2S_SY; ++i) {
-            if (Ys + i >= H) break;                                  // warp-uniform
-            const int y0 = y0s[i], y1 = y0 + (y0 < h - 1);
-            if (y0 != cur_y0) {                                      // warp-uniform: every lane of a warp has the same crop row
-                if (y0 == cur_y1) {
-#pragma unroll
-                    for (int q = 0; q < CP / 2; ++q) top[q] = bot[q];
-                } else {
-                    const int ro = (y0 - ys0) * in_tw * CP;
-                    hlerp_row<CP>(tm + ro + c0, tm + ro + c1, hx, lx, top);
-                }
-                if (y1 == y0) {
-#pragma unroll
-                    for (int q = 0; q < CP / 2; ++q) bot[q] = top[q];
-                } else {
-                    const int ro = (y1 - ys0) * in_tw * CP;
-                    hlerp_row<CP>(tm + ro + c0, tm + ro + c1, hx, lx, bot);
-                }
-                cur_y0 = y0;
-                cur_y1 = y1;
-            }
-            float cf;
-            int lab;
-            vlerp_softmax_max<CT>(top, bot, C, hys[i], lys[i], tm_mode, temp, rtemp, cf, lab);
-            const size_t o = ((size_t)b * H + (Ys + i)) * W + X;
-            if (conf_out) conf_out[o] = cf;
-            if (label_out) label_out[o] = lab;
-            if (map == 0) lr[i] = lab;
-            else lc[i] = lab;
-        }
-    }
-    if (fused && fuse_mode == CSS_FUSE_MIX) {
-#pragma unroll
-        for (int i = 0; i < K2S_SY; ++i)
-            if (Ys + i < H) fused[((size_t)b * H + (Ys + i)) * W + X] = (lr[i] == lc[i]) ? (float)lc[i] : 255.f;   // ddp_model.py:115-118
-    }
-}
-
-// un-staged fallback (strong down-sampling: the footprint of a tile does not fit in shared memory): taps from global memory
-__global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
-    const float* __restrict__ sim, const float* __restrict__ logits, float temp, float rtemp, int tmode, int fuse_mode, int C, int h, int w, int H, int W,
-    float ry, float rx, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
-    int64_t* __restrict__ label_cls, float* __restrict__ fused) {
-    const int b = blockIdx.z;
-    const int Y = blockIdx.y * K2_TH + (threadIdx.x >> 5), X = blockIdx.x * K2_TW + (threadIdx.x & 31);
-    const int hw = h * w;
     if (Y >= H || X >= W) return;
     Taps t;
     {
@@ -641,22 +550,24 @@ __global__ void __launch_bounds__(K2_TH * K2_TW) upsample_label_fuse_kernel(
         t.hy = __fsub_rn(1.f, t.ly);
         t.lx = __fsub_rn(xs, (float)x0);
         t.hx = __fsub_rn(1.f, t.lx);
-        t.o00 = y0 * w + x0;
-        t.o01 = y0 * w + x1;
-        t.o10 = y1 * w + x0;
-        t.o11 = y1 * w + x1;
+        t.o00 = (y0 - ys0) * in_tw + (x0 - xs0);
+        t.o01 = (y0 - ys0) * in_tw + (x1 - xs0);
+        t.o10 = (y1 - ys0) * in_tw + (x0 - xs0);
+        t.o11 = (y1 - ys0) * in_tw + (x1 - xs0);
     }
     const size_t o = ((size_t)b * H + Y) * W + X;
     int lr = -1, lc = -2;
     if (sim) {
         float cf;
-        upsample_softmax_max<0>(sim + (size_t)b * C * hw, C, hw, t, tmode, temp, rtemp, cf, lr);
+        if (STAGED) upsample_softmax_max_tile<CT>(tile, C, t, tmode, temp, rtemp, cf, lr);
+        else upsample_softmax_max<CT>(sim + (size_t)b * C * hw, C, hw, t, tmode, temp, rtemp, cf, lr);
         if (conf_rep) conf_rep[o] = cf;
         if (label_rep) label_rep[o] = lr;
     }
     if (logits) {
         float cf;
-        upsample_softmax_max<0>(logits + (size_t)b * C * hw, C, hw, t, 0, 1.f, 1.f, cf, lc);
+        if (STAGED) upsample_softmax_max_tile<CT>(tile + (size_t)tile_cap * (CT > 0 ? ((CT + 3) & ~3) : CSS_CMAX), C, t, 0, 1.f, 1.f, cf, lc);
+        else upsample_softmax_max<CT>(logits + (size_t)b * C * hw, C, hw, t, 0, 1.f, 1.f, cf, lc);
         if (conf_cls) conf_cls[o] = cf;
         if (label_cls) label_cls[o] = lc;
     }
@@ -678,37 +589,35 @@ extern "C" int css_upsample_label_fuse(const float* sim, const float* logits, fl
     // area_pixel_compute_scale(align_corners=True): (in-1)/(out-1) in fp32, 0 when out == 1
     const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    // upper bound of the low-res footprint of one K2S_TH x K2S_TW output tile (+1 of slack for fp32 rounding of src indices)
-    const int in_th = (int)fminf((float)h, ceilf(ry * (K2S_TH - 1)) + 3.f);
-    const int in_tw = (int)fminf((float)w, ceilf(rx * (K2S_TW - 1)) + 3.f);
+    // upper bound of the low-res footprint of one 8 x 32 output tile (+1 of slack for fp32 rounding of src indices)
+    const int in_th = (int)fminf((float)h, ceilf(ry * (K2_TH - 1)) + 3.f);
+    const int in_tw = (int)fminf((float)w, ceilf(rx * (K2_TW - 1)) + 3.f);
     const int tile_cap = in_th * in_tw;
     const int cp = (C == 21 || C == 19) ? ((C + 3) & ~3) : CSS_CMAX;       // class pitch of the staged tile (see the kernel)
     const size_t smem = (size_t)2 * cp * tile_cap * sizeof(float);
+    dim3 grid((W + K2_TW - 1) / K2_TW, (H + K2_TH - 1) / K2_TH, B);
     cudaStream_t st = (cudaStream_t)stream;
     // x / temp == x * (1/temp) exactly when temp is a power of two (the shipped 0.5 / 0.25); otherwise divide like the reference
     int texp;
     const int tmode = (frexpf(temp, &texp) == 0.5f) ? 1 : 2;
     const float rtemp = 1.f / temp;
+#define K2_LAUNCH(STG, CTV, SM)                                                                                                     \
+    upsample_label_fuse_kernel<STG, CTV><<<grid, K2_TH * K2_TW, SM, st>>>(sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, \
+                                                                         rx, tile_cap, conf_rep, label_rep, conf_cls, label_cls, fused)
     if (smem <= 96 * 1024) {
-        dim3 grid((W + K2S_TW - 1) / K2S_TW, (H + K2S_TH - 1) / K2S_TH, B);
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(upsample_label_fuse_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_strip_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_strip_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(upsample_label_fuse_kernel<true, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) { css_set_error("css_upsample_label_fuse: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         }
-#define K2_LAUNCH(CTV)                                                                                                                  \
-    upsample_label_fuse_strip_kernel<CTV><<<grid, K2S_STRIPS * K2S_TW, smem, st>>>(sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, \
-                                                                                  rx, tile_cap, conf_rep, label_rep, conf_cls, label_cls, fused)
-        if (C == 21) K2_LAUNCH(21);          // VOC
-        else if (C == 19) K2_LAUNCH(19);     // CityScapes
-        else K2_LAUNCH(0);
-#undef K2_LAUNCH
+        if (C == 21) K2_LAUNCH(true, 21, smem);          // VOC
+        else if (C == 19) K2_LAUNCH(true, 19, smem);     // CityScapes
+        else K2_LAUNCH(true, 0, smem);
     } else {   // strong down-sampling: the footprint does not fit, read the taps from global memory
-        dim3 grid((W + K2_TW - 1) / K2_TW, (H + K2_TH - 1) / K2_TH, B);
-        upsample_label_fuse_kernel<<<grid, K2_TH * K2_TW, 0, st>>>(sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, rx, conf_rep,
-                                                                  label_rep, conf_cls, label_cls, fused);
+        K2_LAUNCH(false, 0, 0);
     }
+#undef K2_LAUNCH
     CSS_CHECK_LAUNCH("css_upsample_label_fuse", 1);
     return 0;
 }

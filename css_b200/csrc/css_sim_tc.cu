@@ -13,32 +13,45 @@
 // truncation, which biases long chains; the 256-channel contraction is therefore cut into four 64-channel accumulators (8 MMAs
 // each) plus one accumulator for the two correction terms, summed by the epilogue in fp32.
 //
-// Shape of one CTA (512 threads, one per SM, persistent over 128-pixel tiles):
-//   * warp w = (pixel group w & 3, channel quarter w >> 2): lane = one pixel, 16 consecutive channels of the current 64-channel
-//     chunk: 16 independent 4-byte loads in flight for the NEXT chunk while the current one is split and staged;
-//   * A stage in shared memory: K-major SWIZZLE_128B (row = pixel, 128 B = 32 channels, 8-row atoms of 1 KB), the layout the
-//     tensor core reads without transposition: a thread's 16 channels are 64 contiguous bytes of its pixel's row, i.e. four
-//     128-bit stores per half, and the XOR swizzle spreads the 8 pixels of a store phase over all banks; two stages
-//     (hi | lo, 64 KB each).  (An MN-major A descriptor -- pixels contiguous, as the NCHW planes are -- returned zeros for
-//     kind::tf32 in every canonical layout tried on B200, tools/dev/dev_umma.cu; K-major is also the cheaper store pattern.)
-//   * B (32 class slots x 256 channels, K-major SWIZZLE_128B, hi | lo = 64 KB) is written once per call in exactly the shared
-//     memory image by proto_prep_tc_kernel and copied in at kernel start;
-//   * thread 0 issues the 24 MMAs of a chunk after the CTA barrier (M = 128, N = 32, K = 8 each) and commits them to the
-//     stage's mbarrier; the stage is reused when that barrier completes;
-//   * epilogue (warps 0-3, lane = TMEM lane = pixel): tcgen05.ld of the five accumulators, 1 / max(||x||, 1e-12), optional
-//     softmax, coalesced NCHW stores; the pixel-major rows leave registers as whole 32-byte sectors, as in css_sim.cu.
+// Shape of one CTA (704 threads, one per SM, persistent over tiles of <= 128 consecutive pixels of ONE image), warp-specialised,
+// mbarrier-paced, no CTA-wide barrier in the loop:
+//   * loader warp: the map comes in with 1-D bulk copies (cp.async.bulk global -> shared, completion on an mbarrier).  The NCHW
+//     planes are only 4-byte aligned (h*w is odd), a bulk copy needs 16-byte alignment, so lane d copies the 16-byte-aligned
+//     WINDOW that covers the tile's 128 pixels of plane d (<= 528 bytes) and the readers skip the 0 / 4 / 8 / 12 bytes of lead-in.
+//     Four 32-channel chunks (4 x 16.5 KB) are in flight per CTA, tracked by the barrier's transaction count -- not by registers
+//     and scoreboards (a register ring of the same depth ran at one memory latency per chunk) and not by 4-byte cp.async (LDGSTS
+//     issue alone took longer than the FFMA2 kernel); 512-byte bursts per plane instead of 128-byte warp requests;
+//   * 16 producer warps, warp w = (pixel group w & 3, channel octet w >> 2): lane = one pixel, 8 consecutive channels of the chunk:
+//     reads its own 8 raw values, splits them into TF32 hi / lo, stores them K-major SWIZZLE_128B (row = pixel, 128 B = 32
+//     channels: two 128-bit stores per half; the XOR swizzle spreads the 8 pixels of a store phase over all banks) and writes
+//     its 32 bytes of the pixel-major row as one whole sector;
+//     (an MN-major A descriptor -- pixels contiguous, as the NCHW planes are -- returned zeros for kind::tf32 in every
+//     canonical layout tried on B200, tools/dev/dev_umma.cu; K-major is also the cheaper store pattern)
+//   * two A operand stages (hi | lo, 32 KB each); B (32 class slots x 256 channels, K-major SWIZZLE_128B, hi | lo = 64 KB) is
+//     written once per call in exactly the shared-memory image by proto_prep_tc_kernel and copied in at kernel start;
+//   * one MMA warp: waits for a stage to be full, issues its 12 MMAs (M = 128, N = 32, K = 8), commits them to the stage's
+//     "empty" barrier; the accumulators are double-buffered in TMEM (2 x 160 columns), so the next tile's MMAs run while
+//   * four epilogue warps (lane = TMEM lane = pixel) read the previous tile: tcgen05.ld of the five accumulators,
+//     1 / max(||x||, 1e-12), optional softmax, coalesced NCHW stores, norms.
 #include "css_common.cuh"
 
-#define TC_THREADS 512
+#define TC_PRODUCERS 512               // 16 producer warps
+#define TC_THREADS (TC_PRODUCERS + 4 * 32 + 32 + 32)    // + 4 epilogue warps + MMA warp + loader warp
 #define TC_M 128                      // pixels per tile  (UMMA M)
 #define TC_N 32                       // class slots      (UMMA N)
-#define TC_KC 64                      // channels per chunk (= per shared-memory stage)
-#define TC_NCHUNK (CSS_D / TC_KC)     // 4 chunks per tile, one main accumulator each
-#define TC_U 16                       // channels per thread per chunk
-#define TC_STAGE_HALF (TC_KC * TC_M * 4)          // 32 KB: hi (or lo) part of one stage
+#define TC_KC 32                      // channels per chunk (= per shared-memory stage = one 128-byte swizzle row)
+#define TC_NCHUNK (CSS_D / TC_KC)     // 8 chunks per tile
+#define TC_NACC 4                     // main accumulators per tile (two chunks = 64 channels = 8 MMAs each)
+#define TC_U 8                        // channels per producer thread per chunk
+#define TC_STAGES 2                   // K-major hi | lo operand stages (the MMAs drain a stage in a few hundred cycles)
+#define TC_RAW 4                      // raw fp32 chunks in flight per CTA
+#define TC_RAW_PITCH (TC_M * 4 + 16)  // bytes per plane window: 128 pixels + up to 12 bytes of lead-in, rounded to 16
+#define TC_RAW_BYTES (TC_KC * TC_RAW_PITCH)       // 16.5 KB per raw chunk
+#define TC_STAGE_HALF (TC_KC * TC_M * 4)          // 16 KB: hi (or lo) part of one stage
 #define TC_B_HALF (TC_N * CSS_D * 4)              // 32 KB: hi (or lo) image of the prototypes
-#define TC_TMEM_COLS 256                          // 5 accumulators x 32 columns, rounded up to a power of two
-#define TC_SMEM_BYTES (2 * TC_B_HALF + 2 * 2 * TC_STAGE_HALF + 4096 + 1024)   // B | 2 stages | barriers + norm partials | align
+#define TC_ACC_COLS ((TC_NACC + 1) * TC_N)        // 160 columns per accumulator buffer
+#define TC_TMEM_COLS 512                          // two buffers, rounded up to a power of two
+#define TC_SMEM_BYTES (2 * TC_B_HALF + TC_STAGES * 2 * TC_STAGE_HALF + TC_RAW * TC_RAW_BYTES + 4096 + 1024)   // B | stages | raw ring | state | align
 
 // ---------------------------------------------------------------------------------------------------------------------
 // shared-memory images
@@ -141,38 +154,65 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TcShared {                     // small state behind the big buffers
-    unsigned long long mma_done[2];   // stage s may be overwritten: the MMAs that read it have completed
-    unsigned long long acc_full;      // the tile's accumulators are complete
+    unsigned long long raw_full[TC_RAW];   // loader -> producers: the raw chunk has landed     (1 arrival + transaction bytes)
+    unsigned long long raw_empty[TC_RAW];  // producers -> loader: the raw chunk has been read  (16 warp arrivals)
+    unsigned long long full[TC_STAGES];    // producers -> MMA warp: the stage holds a chunk    (16 warp arrivals)
+    unsigned long long empty[TC_STAGES];   // MMA warp -> producers: the MMAs that read the stage are done (tcgen05.commit)
+    unsigned long long acc_full[2];        // MMA warp -> epilogue: the tile's accumulators are complete (tcgen05.commit)
+    unsigned long long acc_empty[2];       // epilogue -> MMA warp: the buffer has been read               (4 warp arrivals)
+    unsigned long long n2_full[2];         // producers -> epilogue: the tile's norm partials are written  (16 warp arrivals)
     uint32_t tmem_base;
     uint32_t pad;
-    float n2[4][TC_M];                // per channel quarter partial ||x||^2
+    float n2[2][4][TC_M];                  // [tile parity][channel octet of the chunk][pixel] partial ||x||^2
 };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
-// NP: 8-column parts of the accumulators the epilogue reads (3 when C <= 24, else 4)
+// Tile t = (image b = t / tpi, pixels s0 = (t % tpi) * 128 .. of that image): a tile never straddles two images, so the 128
+// pixels of a plane are one contiguous run.  NP: 8-column parts of the accumulators the epilogue reads (3 when C <= 24, else 4).
 template <bool ROWS, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float* __restrict__ rep, const char* __restrict__ b_image, int hw,
-                                                                    int N, int C, int mode, float temp, float* __restrict__ out,
+                                                                    int n_img, int C, int mode, float temp, float* __restrict__ out,
                                                                     float* __restrict__ rows, float* __restrict__ norms) {
     extern __shared__ char smem_raw[];
     char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms: 1 KB aligned
     char* sB = smem;                                        // [hi 32 KB | lo 32 KB]
-    char* sA = smem + 2 * TC_B_HALF;                        // stage s at s * 64 KB: [hi 32 KB | lo 32 KB]
-    TcShared* sh = reinterpret_cast<TcShared*>(sA + 2 * 2 * TC_STAGE_HALF);
+    char* sA = smem + 2 * TC_B_HALF;                        // stage s at s * 32 KB: [hi 16 KB | lo 16 KB]
+    char* sR = sA + TC_STAGES * 2 * TC_STAGE_HALF;         // raw ring: slot r at r * 16.5 KB, plane window d at d * TC_RAW_PITCH
+    TcShared* sh = reinterpret_cast<TcShared*>(sR + TC_RAW * TC_RAW_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pg = warp & 3, cq = warp >> 2;
-    const int m = pg * 32 + lane;                           // pixel of the tile = TMEM lane = row of A
+    constexpr int MMA_WARP = TC_PRODUCERS / 32 + 4, LOAD_WARP = MMA_WARP + 1;
 
     // ---- one-time set-up: barriers, tensor memory, the prototype image ----
     if (tid == 0) {
-        mbar_init(smem_u32(&sh->mma_done[0]), 1);
-        mbar_init(smem_u32(&sh->mma_done[1]), 1);
-        mbar_init(smem_u32(&sh->acc_full), 1);
+        for (int i = 0; i < TC_RAW; ++i) {
+            mbar_init(smem_u32(&sh->raw_full[i]), 1);
+            mbar_init(smem_u32(&sh->raw_empty[i]), TC_PRODUCERS / 32);
+        }
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(smem_u32(&sh->full[i]), TC_PRODUCERS / 32);
+            mbar_init(smem_u32(&sh->empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&sh->acc_full[i]), 1);
+            mbar_init(smem_u32(&sh->acc_empty[i]), 4);
+            mbar_init(smem_u32(&sh->n2_full[i]), TC_PRODUCERS / 32);
+        }
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -186,120 +226,151 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float*
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh->tmem_base;
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const int tpi = (hw + TC_M - 1) / TC_M;                 // tiles per image
+    const int n_tiles = n_img * tpi;
+    const uintptr_t rep_begin = reinterpret_cast<uintptr_t>(rep), rep_end = rep_begin + (size_t)n_img * CSS_D * hw * 4;
 
-    const int n_tiles = (N + TC_M - 1) / TC_M;
-    // byte offset of this thread's pixel row inside a stage half (K-major SWIZZLE_128B: 32-channel blocks of 128 x 128 B = 16 KB,
-    // 8-row atoms of 1 KB): its 16 channels cq*16.. are the 16-byte chunks (cq & 1)*4 + j of block cq >> 1, XOR-swizzled by m & 7
-    const uint32_t a_thread = (uint32_t)((cq >> 1) * (TC_M * 128) + (m >> 3) * 1024 + (m & 7) * 128);
-    const int chunk0 = (cq & 1) * 4, r7 = m & 7;
-
-    float cur[TC_U], nxt[TC_U];
-    const float* xp = nullptr;                              // first channel of this thread in the current tile
-    auto tile_ptr = [&](int tile) -> const float* {
-        const int p = min(tile * TC_M + m, N - 1);          // out-of-range lanes re-read the last pixel, never write
-        const int b = p / hw;
-        return rep + ((size_t)b * CSS_D + cq * TC_U) * hw + (p - b * hw);
-    };
-    auto load_chunk = [&](const float* base, int ch, float (&v)[TC_U]) {
-        const float* p = base + (size_t)(ch * TC_KC) * hw;
-#pragma unroll
-        for (int u = 0; u < TC_U; ++u, p += hw) v[u] = ldg_stream(p);
-    };
-
-    int tile = blockIdx.x;
-    if (tile < n_tiles) {
-        xp = tile_ptr(tile);
-        load_chunk(xp, 0, cur);
-    }
-    uint32_t g = 0;                                         // chunks this CTA has staged so far (stage = g & 1)
-    uint32_t tile_it = 0;
-    for (; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-        const int pix = tile * TC_M + m;
-        float n2 = 0.f;
-        const int next_tile = tile + gridDim.x;
-        const float* xp_next = next_tile < n_tiles ? tile_ptr(next_tile) : nullptr;
-#pragma unroll
-        for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
-            // 1. the next chunk's loads go out before anything else touches the current one
-            if (ch + 1 < TC_NCHUNK) load_chunk(xp, ch + 1, nxt);
-            else if (xp_next) load_chunk(xp_next, 0, nxt);
-            // 2. the stage is free once the MMAs of its previous use have completed
-            const uint32_t stage = g & 1u;
-            if (g >= 2) mbar_wait(smem_u32(&sh->mma_done[stage]), ((g >> 1) - 1u) & 1u);
-            // 3. split into TF32 hi / lo and stage K-major (the thread's 16 channels = four 16-byte chunks of its pixel's row)
-            char* st_hi = sA + stage * (2 * TC_STAGE_HALF) + a_thread;
-            char* st_lo = st_hi + TC_STAGE_HALF;
-#pragma unroll
-            for (int j = 0; j < TC_U / 4; ++j) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float x = cur[4 * j + e];
-                    hi[e] = rna_tf32(x);
-                    lo[e] = rna_tf32(__fsub_rn(x, __uint_as_float(hi[e])));
-                    n2 = fmaf(x, x, n2);
+    if (warp == LOAD_WARP) {
+        // =========================================== loader ===========================================
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int b = tile / tpi, s0 = (tile - b * tpi) * TC_M, len = min(TC_M, hw - s0);
+            for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                const uint32_t rslot = g & (TC_RAW - 1), use = g / TC_RAW;
+                if (use > 0) mbar_wait(smem_u32(&sh->raw_empty[rslot]), (use - 1u) & 1u);
+                // lane d: the aligned window of plane ch*32 + d that covers pixels s0 .. s0 + len
+                const uintptr_t src = rep_begin + ((size_t)(b * CSS_D + ch * TC_KC + lane) * hw + s0) * 4;
+                const uintptr_t src_al = src & ~(uintptr_t)15;
+                uint32_t bytes = (uint32_t)(((src - src_al) + (size_t)len * 4 + 15) & ~(size_t)15);
+                const uint32_t dst = smem_u32(sR) + rslot * TC_RAW_BYTES + lane * TC_RAW_PITCH;
+                const uint32_t bar = smem_u32(&sh->raw_full[rslot]);
+                const bool inside = src_al >= rep_begin && src_al + bytes <= rep_end;       // never read outside the tensor
+                if (!inside) {                                   // (at most the first and the last plane of the whole map)
+                    float* d = reinterpret_cast<float*>(sR + rslot * TC_RAW_BYTES + lane * TC_RAW_PITCH + (src - src_al));
+                    const float* sp = reinterpret_cast<const float*>(src);
+                    for (int i = 0; i < len; ++i) d[i] = sp[i];
+                    bytes = 0;
                 }
-                const uint32_t off = (uint32_t)(((chunk0 + j) ^ r7) << 4);
-                *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            // 4. pixel-major rows: a lane holds 64 contiguous bytes of its pixel's row; lane pairs swap 16-byte chunks so that
-            //    every 128-bit store instruction completes whole 32-byte sectors
-            if (ROWS) {
-                const int odd = lane & 1;
-                const int pA = pix - odd, pB = pA + 1;
-                float* rA = rows + (size_t)pA * CSS_D + ch * TC_KC + cq * TC_U + 4 * odd;
-                float* rB = rA + CSS_D;
+                uint32_t total = bytes;
 #pragma unroll
-                for (int hh = 0; hh < TC_U / 8; ++hh) {
-                    const int ue = 8 * hh, uo = 8 * hh + 4;
-                    const float4 own_e = make_float4(cur[ue], cur[ue + 1], cur[ue + 2], cur[ue + 3]);
-                    const float4 own_o = make_float4(cur[uo], cur[uo + 1], cur[uo + 2], cur[uo + 3]);
-                    const float4 snd = odd ? own_e : own_o;
-                    float4 rcv;
-                    rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1);
-                    rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
-                    rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1);
-                    rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
-                    const float4 first = odd ? rcv : own_e;
-                    const float4 second = odd ? own_o : rcv;
-                    if (pA < N) *reinterpret_cast<float4*>(rA + 8 * hh) = first;
-                    if (pB < N) *reinterpret_cast<float4*>(rB + 8 * hh) = second;
-                }
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(bar, total);
+                __syncwarp();
+                if (inside) bulk_g2s(dst, reinterpret_cast<const void*>(src_al), bytes, bar);
             }
-            if (ch == TC_NCHUNK - 1) sh->n2[cq][m] = n2;
-            // 5. make the staged operands visible to the tensor core (async proxy), then one thread issues the chunk's MMAs
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t a_hi = sA_u + stage * (2 * TC_STAGE_HALF), a_lo = a_hi + TC_STAGE_HALF;
-#pragma unroll
-                for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                    const uint32_t k = (uint32_t)(ch * TC_KC + ks * 8);
-                    const uint32_t b_off = (k >> 5) * 4096 + ((k & 31) >> 3) * 32;
-                    const uint32_t a_off = (uint32_t)((ks >> 2) * (TC_M * 128) + (ks & 3) * 32);
-                    const uint64_t da_hi = umma_desc(a_hi + a_off, 16, 1024), da_lo = umma_desc(a_lo + a_off, 16, 1024);
-                    const uint64_t db_hi = umma_desc(sB_u + b_off, 16, 1024), db_lo = umma_desc(sB_u + TC_B_HALF + b_off, 16, 1024);
-                    umma_tf32(tmem + ch * TC_N, da_hi, db_hi, ks > 0);                         // main: 64 channels per accumulator
-                    umma_tf32(tmem + TC_NCHUNK * TC_N, da_lo, db_hi, (ch | ks) != 0);          // corrections share one accumulator
-                    umma_tf32(tmem + TC_NCHUNK * TC_N, da_hi, db_lo, 1);
-                }
-                umma_commit(smem_u32(&sh->mma_done[stage]));
-                if (ch == TC_NCHUNK - 1) umma_commit(smem_u32(&sh->acc_full));
-            }
-#pragma unroll
-            for (int u = 0; u < TC_U; ++u) cur[u] = nxt[u];
         }
-        xp = xp_next;
-        // ---- epilogue: lane = TMEM lane = pixel ----
-        if (cq == 0) {
-            mbar_wait(smem_u32(&sh->acc_full), tile_it & 1u);
+    } else if (warp < TC_PRODUCERS / 32) {
+        // =========================================== producers ===========================================
+        const int pg = warp & 3, co = warp >> 2;            // pixel group, channel octet of every chunk
+        const int m = pg * 32 + lane;                       // pixel of the tile = row of A
+        // this thread's pixel row inside a stage half (K-major SWIZZLE_128B, 8-row atoms of 1 KB); its 8 channels are the
+        // 16-byte chunks 2*co, 2*co + 1 of the row, XOR-swizzled by m & 7
+        const uint32_t a_row = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+        const uint32_t off0 = (uint32_t)(((2 * co) ^ (m & 7)) << 4), off1 = (uint32_t)(((2 * co + 1) ^ (m & 7)) << 4);
+        const int hw3 = hw & 3, base16 = (int)(rep_begin & 15);
+        uint32_t g = 0;                                     // chunks staged so far by this CTA
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const int b = tile / tpi, s0 = (tile - b * tpi) * TC_M, len = min(TC_M, hw - s0);
+            const bool live = m < len;
+            const int pix = b * hw + s0 + m;
+            // lead-in of the plane windows: plane index mod 4 == u mod 4 for this thread's channel u (b*256, ch*32, co*8 are
+            // multiples of 4), so the misalignment of its 8 windows takes 4 values per tile
+            int lead[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lead[q] = (base16 + 4 * ((q * hw3 + s0) & 3)) & 15;
+            float n2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                const int rslot = ch & (TC_RAW - 1);        // == g % TC_RAW: TC_NCHUNK is a multiple of TC_RAW
+                const uint32_t slot = g & (TC_STAGES - 1), use = g / TC_STAGES;
+                mbar_wait(smem_u32(&sh->raw_full[rslot]), (g / TC_RAW) & 1u);
+                float x[TC_U];
+                {
+                    const char* rp = sR + rslot * TC_RAW_BYTES + (co * TC_U) * TC_RAW_PITCH + m * 4;
+#pragma unroll
+                    for (int u = 0; u < TC_U; ++u)
+                        x[u] = live ? *reinterpret_cast<const float*>(rp + u * TC_RAW_PITCH + lead[u & 3]) : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh->raw_empty[rslot]));       // the loader may refill the raw slot
+                // pixel-major rows: the thread's 8 channels are one whole 32-byte sector of its pixel's row
+                if (ROWS && live) {
+                    float4* r = reinterpret_cast<float4*>(rows + (size_t)pix * CSS_D + ch * TC_KC + co * TC_U);
+                    r[0] = make_float4(x[0], x[1], x[2], x[3]);
+                    r[1] = make_float4(x[4], x[5], x[6], x[7]);
+                }
+                uint32_t hi[TC_U], lo[TC_U];
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    hi[u] = rna_tf32(x[u]);
+                    lo[u] = rna_tf32(__fsub_rn(x[u], __uint_as_float(hi[u])));
+                    n2 = fmaf(x[u], x[u], n2);
+                }
+                // the operand stage is free once the MMAs of its previous use have completed
+                if (use > 0) mbar_wait(smem_u32(&sh->empty[slot]), (use - 1u) & 1u);
+                char* st_hi = sA + slot * (2 * TC_STAGE_HALF) + a_row;
+                char* st_lo = st_hi + TC_STAGE_HALF;
+                *reinterpret_cast<uint4*>(st_hi + off0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(st_hi + off1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<uint4*>(st_lo + off0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(st_lo + off1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                if (ch == TC_NCHUNK - 1) sh->n2[tile_it & 1u][co][m] = n2;
+                fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&sh->full[slot]));
+                    if (ch == TC_NCHUNK - 1) mbar_arrive(smem_u32(&sh->n2_full[tile_it & 1u]));
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================== MMA issuer ===========================================
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        uint32_t g = 0;
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t buf = tile_it & 1u, d_base = tmem + buf * TC_ACC_COLS;
+            if (tile_it >= 2) mbar_wait(smem_u32(&sh->acc_empty[buf]), ((tile_it >> 1) - 1u) & 1u);
+            tc_fence_after();
+            for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                const uint32_t slot = g & (TC_STAGES - 1), use = g / TC_STAGES;
+                mbar_wait(smem_u32(&sh->full[slot]), use & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = sA_u + slot * (2 * TC_STAGE_HALF), a_lo = a_hi + TC_STAGE_HALF;
+                    const uint32_t b_blk = (uint32_t)ch * 4096;                                  // 32-channel block of the prototype image
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        const uint64_t da_hi = umma_desc(a_hi + ks * 32, 16, 1024), da_lo = umma_desc(a_lo + ks * 32, 16, 1024);
+                        const uint64_t db_hi = umma_desc(sB_u + b_blk + ks * 32, 16, 1024), db_lo = umma_desc(sB_u + TC_B_HALF + b_blk + ks * 32, 16, 1024);
+                        umma_tf32(d_base + (ch >> 1) * TC_N, da_hi, db_hi, ((ch & 1) | ks) != 0);     // main: 64 channels per accumulator
+                        umma_tf32(d_base + TC_NACC * TC_N, da_lo, db_hi, (ch | ks) != 0);              // corrections share one accumulator
+                        umma_tf32(d_base + TC_NACC * TC_N, da_hi, db_lo, 1);
+                    }
+                    umma_commit(smem_u32(&sh->empty[slot]));
+                    if (ch == TC_NCHUNK - 1) umma_commit(smem_u32(&sh->acc_full[buf]));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================================== epilogue ===========================================
+        const int pg = warp & 3;                            // warps 16..19: TMEM lane quarter = warp % 4
+        const int m = pg * 32 + lane;
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t buf = tile_it & 1u, par = (tile_it >> 1) & 1u;
+            const int b = tile / tpi, s0 = (tile - b * tpi) * TC_M, len = min(TC_M, hw - s0);
+            const int s = s0 + m, pix = b * hw + s;
+            mbar_wait(smem_u32(&sh->n2_full[buf]), par);
+            const float* n2p = &sh->n2[buf][0][m];
+            const float n2 = (n2p[0] + n2p[TC_M]) + (n2p[2 * TC_M] + n2p[3 * TC_M]);
+            mbar_wait(smem_u32(&sh->acc_full[buf]), par);
             tc_fence_after();
             float val[NP * 8];
-            const uint32_t t_lane = tmem + ((uint32_t)(pg * 32) << 16);
+            const uint32_t t_lane = tmem + buf * TC_ACC_COLS + ((uint32_t)(pg * 32) << 16);
 #pragma unroll
             for (int part = 0; part < NP; ++part) {             // pairwise, to keep few accumulator registers live
                 float a0[8], a1[8], s01[8];
@@ -319,8 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float*
                 for (int i = 0; i < 8; ++i) val[part * 8 + i] = s01[i] + a0[i];
             }
             tc_fence_before();
-            if (pix < N) {
-                const float nrm_raw = sqrtf((sh->n2[0][m] + sh->n2[1][m]) + (sh->n2[2][m] + sh->n2[3][m]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sh->acc_empty[buf]));      // the MMA warp may overwrite this buffer
+            if (m < len) {
+                const float nrm_raw = sqrtf(n2);
                 if (ROWS) norms[pix] = nrm_raw;
                 const float inv = mode == 2 ? 1.f : __frcp_rn(fmaxf(nrm_raw, 1e-12f));      // mode 2 (diagnostic): raw x . p_hat
 #pragma unroll
@@ -341,7 +414,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float*
 #pragma unroll
                     for (int c = 0; c < NP * 8; ++c) val[c] *= inv_sum;
                 }
-                const int b = pix / hw, s = pix - b * hw;
                 float* o = out + (size_t)b * C * hw + s;
 #pragma unroll
                 for (int c = 0; c < NP * 8; ++c)
@@ -349,10 +421,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float*
             }
         }
     }
-    // ---- teardown: every MMA has completed (the last acc_full was waited for), release tensor memory ----
+    // ---- teardown: all roles are done (the epilogue waited for the last accumulators), release tensor memory ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
     }
@@ -361,10 +433,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float*
 // host side: returns 0 if the tensor-core pass was launched, <0 / >0 on error
 int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scratch, int B, int C, int h, int w, int mode, float temp,
                     float* sim_out, float* rows, float* norms, cudaStream_t st) {
-    const int hw = h * w, N = B * hw;
+    const int hw = h * w;
     char* image = reinterpret_cast<char*>(proto_scratch);
     proto_prep_tc_kernel<<<TC_N, CSS_D, 0, st>>>(prototypes, image, C);
-    const int n_tiles = (N + TC_M - 1) / TC_M;
+    const int n_tiles = B * ((hw + TC_M - 1) / TC_M);
     const int sms = css_cached_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     cudaError_t e;
@@ -372,7 +444,7 @@ int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scra
     do {                                                                                                                              \
         e = cudaFuncSetAttribute(rep_pass_tc_kernel<ROWS_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);          \
         if (e == cudaSuccess)                                                                                                         \
-            rep_pass_tc_kernel<ROWS_, NP_><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(rep, image, hw, N, C, mode, temp, sim_out, rows, norms); \
+            rep_pass_tc_kernel<ROWS_, NP_><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(rep, image, hw, B, C, mode, temp, sim_out, rows, norms); \
     } while (0)
     if (rows) {
         if (C <= 24) TC_LAUNCH(true, 3);

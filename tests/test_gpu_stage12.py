@@ -127,3 +127,34 @@ def test_threshold_glue_exact_against_oracle(strategy, B, C, H, W, h, w):
     la, ma = css_b200.ops.threshold_glue(ll.cuda(), lu.cuda(), conf.cuda(), 0.7, C, (h, w), strategy)
     la_ref, ma_ref = O.threshold_glue(ll.numpy(), lu.numpy(), conf.numpy(), 0.7, C, (h, w), strategy)
     assert np.array_equal(la.cpu().numpy(), la_ref) and np.array_equal(ma.cpu().numpy(), ma_ref)
+
+
+@pytest.mark.parametrize("B,C,h,w", [(8, 21, 81, 81), (4, 19, 193, 193), (3, 32, 20, 21), (1, 5, 7, 9), (2, 21, 33, 31)])
+def test_tensor_core_rep_pass_matches_oracle_and_fma_path(B, C, h, w):
+    """css_rep_pass has two multiply sides for fp32 maps: packed FFMA2 (default) and tcgen05.mma kind::tf32 with TMEM
+    accumulators and an fp32-exact hi/lo operand split (css_sim_tc.cu, opt-in).  Both must meet the same tolerances; the
+    pixel-major rows are a bit-exact copy of the map on either path."""
+    import css_b200
+    from css_b200 import _lib, synth
+    lib = _lib.load()
+    d = synth.student_batch(B, C, h, w, seed=7 + C, block=4)
+    protos = 0.5 * d["centers"] + 0.3 * synth.warm_prototypes(C, seed=3)
+    protos[C // 2] = 0
+    rep = d["rep"].cuda()
+    sim_ref = O.cos_sim_map(d["rep"].numpy(), protos.numpy())
+    prob_ref = O.proto_softmax_sim(d["rep"].numpy(), protos.numpy(), 0.5)
+    got = {}
+    try:
+        for name, flag in (("fma", 0), ("tc", 1)):
+            lib.css_set_rep_pass_path(flag)
+            sim = css_b200.ops.cos_sim_map(rep, protos.cuda())
+            prob = css_b200.ops.proto_softmax_sim(rep, protos.cuda(), 0.5)
+            got[name] = (sim.cpu().numpy(), prob.cpu().numpy(), prob._css_rows.rows, prob._css_rows.norms)
+    finally:
+        lib.css_set_rep_pass_path(-1)
+    for name, (sim, prob, rows, norms) in got.items():
+        np.testing.assert_allclose(sim, sim_ref, rtol=0, atol=1e-6, err_msg=name)
+        np.testing.assert_allclose(prob, prob_ref, rtol=0, atol=1e-6, err_msg=name)
+        assert np.all(sim[:, C // 2] == 0), name
+        assert torch.equal(rows, rep.permute(0, 2, 3, 1).reshape(-1, 256)), name
+        np.testing.assert_allclose(norms.cpu().numpy(), np.linalg.norm(d["rep"].numpy(), axis=1).reshape(-1), rtol=1e-6, err_msg=name)

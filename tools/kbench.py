@@ -40,7 +40,9 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--pool", type=int, default=4)
     ap.add_argument("--bf16", action="store_true", help="bf16 representation maps (bf16 pixel-major rows)")
+    ap.add_argument("--tc", action="store_true", help="tcgen05 rep pass (css_sim_tc.cu) instead of the FFMA2 one")
     a = ap.parse_args()
+    _lib.load().css_set_rep_pass_path(1 if a.tc else 0)
     cfg = WORKLOADS[a.workload]
     B, C, h, w, H, W, Q, Nn, temp = (cfg[k] for k in ("B", "C", "h", "w", "H", "W", "Q", "Nn", "temp"))
     host = make_inputs(cfg, 0)
