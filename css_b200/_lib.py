@@ -29,6 +29,7 @@ SIGNATURES = {
     "css_last_error": (ctypes.c_char_p, []),
     "css_sm_count": (c_int, []),
     "css_launch_count": (ctypes.c_ulonglong, []),
+    "css_set_pdl": (c_int, [c_int]),
     "css_sim_map": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
     "css_upsample_label_fuse": (c_int, [P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "css_select_tiles": (c_int, [c_int]),

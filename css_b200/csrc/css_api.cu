@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error text, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "css_common.cuh"
@@ -23,6 +24,19 @@ int css_cached_sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+static int g_pdl = -1;
+bool css_pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* v = getenv("CSS_B200_PDL");
+        g_pdl = (v && v[0] == '1') ? 1 : 0;      // measured on B200 (r02i): no gain inside CUDA graphs (0.478 vs 0.475 ms/step), so opt-in
+    }
+    return g_pdl != 0;
+}
+extern "C" int css_set_pdl(int on) {
+    g_pdl = on ? 1 : 0;
+    return 0;
 }
 
 static unsigned long long g_launches = 0;

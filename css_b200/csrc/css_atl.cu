@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(ATL_THREADS) atl_forward_kernel(const float* _
                                                                   const float* __restrict__ conf, float thr, int C, int HW,
                                                                   float* __restrict__ lse_out, float* __restrict__ partials,
                                                                   int32_t* __restrict__ counts) {
+    css_pdl_enter();
     __shared__ float wsum[ATL_THREADS / 32];
     __shared__ int wcnt[3][ATL_THREADS / 32];
     const int b = blockIdx.y, p = blockIdx.x * ATL_THREADS + threadIdx.x;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(ATL_THREADS) atl_forward_kernel(const float* _
 // one CTA: per-image loss sums (fixed order), the scalar loss and the per-image backward scale  w_b / #(loss > 0)
 __global__ void __launch_bounds__(256) atl_finalize_kernel(const float* __restrict__ partials, const int32_t* __restrict__ counts, int B,
                                                            int nblk, float* __restrict__ scale, float* __restrict__ loss) {
+    css_pdl_enter();
     __shared__ float img_sum[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int b = warp; b < B; b += 8) {
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(ATL_THREADS) atl_backward_kernel(const float* 
                                                                    const int64_t* __restrict__ label, const float* __restrict__ lse,
                                                                    const float* __restrict__ scale, int C, int HW,
                                                                    float* __restrict__ grad_pred) {
+    css_pdl_enter();
     const int b = blockIdx.y, p = blockIdx.x * ATL_THREADS + threadIdx.x;
     if (p >= HW) return;
     const float* x = pred + (size_t)b * C * HW + p;
@@ -158,10 +161,10 @@ extern "C" int css_atl_forward(const float* pred, const int64_t* label, const fl
     const int HW = H * W, nblk = css_atl_blocks(H, W);
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * B, st);
     if (e != cudaSuccess) { css_set_error("css_atl_forward: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    if (C == 21) atl_forward_kernel<21><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
-    else if (C == 19) atl_forward_kernel<19><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
-    else atl_forward_kernel<0><<<dim3(nblk, B), ATL_THREADS, 0, st>>>(pred, label, conf, threshold, C, HW, lse, partials, counts);
-    atl_finalize_kernel<<<1, 256, 0, st>>>(partials, counts, B, nblk, scale, loss);
+    if (C == 21) css_launch(atl_forward_kernel<21>, dim3(dim3(nblk, B)), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), pred, label, conf, threshold, C, HW, lse, partials, counts);
+    else if (C == 19) css_launch(atl_forward_kernel<19>, dim3(dim3(nblk, B)), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), pred, label, conf, threshold, C, HW, lse, partials, counts);
+    else css_launch(atl_forward_kernel<0>, dim3(dim3(nblk, B)), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), pred, label, conf, threshold, C, HW, lse, partials, counts);
+    css_launch(atl_finalize_kernel, dim3(1), dim3(256), (size_t)(0), (cudaStream_t)(st), partials, counts, B, nblk, scale, loss);
     CSS_CHECK_LAUNCH("css_atl_forward", 2);
     return 0;
 }
@@ -173,9 +176,9 @@ extern "C" int css_atl_backward(const float* grad_out, const float* pred, const 
     const int HW = H * W;
     const dim3 grid(css_atl_blocks(H, W), B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 21) atl_backward_kernel<21><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
-    else if (C == 19) atl_backward_kernel<19><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
-    else atl_backward_kernel<0><<<grid, ATL_THREADS, 0, st>>>(grad_out, pred, label, lse, scale, C, HW, grad_pred);
+    if (C == 21) css_launch(atl_backward_kernel<21>, dim3(grid), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), grad_out, pred, label, lse, scale, C, HW, grad_pred);
+    else if (C == 19) css_launch(atl_backward_kernel<19>, dim3(grid), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), grad_out, pred, label, lse, scale, C, HW, grad_pred);
+    else css_launch(atl_backward_kernel<0>, dim3(grid), dim3(ATL_THREADS), (size_t)(0), (cudaStream_t)(st), grad_out, pred, label, lse, scale, C, HW, grad_pred);
     CSS_CHECK_LAUNCH("css_atl_backward", 1);
     return 0;
 }

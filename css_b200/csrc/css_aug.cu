@@ -11,6 +11,7 @@
 // per (image, axis), <= a few thousand dependent DADDs (~10 us, off the critical path of anything else).
 __global__ void aug_index_kernel(const int* __restrict__ geo, int H, int W, int max_r, int* __restrict__ ymap,
                                  int* __restrict__ xmap) {
+    css_pdl_enter();
     const int b = blockIdx.x, axis = blockIdx.y;
     if (threadIdx.x != 0) return;
     const int n_out = geo[b * AUG_GEO + axis], n_in = axis ? W : H;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) aug_maps_kernel(const LT* __restrict__ la
                                                        const int* __restrict__ xmap, int H, int W, int max_r, int ch, int cw,
                                                        int64_t* __restrict__ ola, int64_t* __restrict__ olb,
                                                        float* __restrict__ oca, float* __restrict__ ocb) {
+    css_pdl_enter();
     const int b = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= cw) return;
     const int* g = geo + b * AUG_GEO;
@@ -62,7 +64,7 @@ extern "C" int css_aug_index(const int32_t* geometry, int B, int H, int W, int m
                              void* stream) {
     CSS_CHECK_ARG(geometry && ymap && xmap, CSS_E_ARG, "css_aug_index: null pointer");
     CSS_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && max_r > 0, CSS_E_ARG, "css_aug_index: non-positive size");
-    aug_index_kernel<<<dim3(B, 2), 32, 0, (cudaStream_t)stream>>>(geometry, H, W, max_r, ymap, xmap);
+    css_launch(aug_index_kernel, dim3(dim3(B, 2)), dim3(32), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), geometry, H, W, max_r, ymap, xmap);
     CSS_CHECK_LAUNCH("css_aug_index", 1);
     return 0;
 }
@@ -82,10 +84,10 @@ extern "C" int css_aug_maps(const void* label_a, const void* label_b, int label_
     const dim3 grid((cw + 255) / 256, ch, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (label_dtype == CSS_LABEL_F32)
-        aug_maps_kernel<float><<<grid, 256, 0, st>>>((const float*)label_a, (const float*)label_b, conf_a, conf_b, geometry, ymap, xmap,
+        css_launch(aug_maps_kernel<float>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(st), (const float*)label_a, (const float*)label_b, conf_a, conf_b, geometry, ymap, xmap,
                                                      H, W, max_r, ch, cw, out_label_a, out_label_b, out_conf_a, out_conf_b);
     else
-        aug_maps_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)label_a, (const int64_t*)label_b, conf_a, conf_b, geometry, ymap,
+        css_launch(aug_maps_kernel<int64_t>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(st), (const int64_t*)label_a, (const int64_t*)label_b, conf_a, conf_b, geometry, ymap,
                                                        xmap, H, W, max_r, ch, cw, out_label_a, out_label_b, out_conf_a, out_conf_b);
     CSS_CHECK_LAUNCH("css_aug_maps", 1);
     return 0;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256) cut_mix_kernel(CutMaps own, CutMaps par, 
                                                       const unsigned long long* __restrict__ class_sets, int mode, int B, int CH,
                                                       int H, int W, float* __restrict__ o_img, int64_t* __restrict__ o_la,
                                                       int64_t* __restrict__ o_lb, float* __restrict__ o_ca, float* __restrict__ o_cb) {
+    css_pdl_enter();
     const int i = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
     const int j = (i + 1) % B;
@@ -144,7 +147,7 @@ extern "C" int css_cut_mix(const float* image, const int64_t* label_a, const int
     CSS_CHECK_ARG((!label_b || out_label_b) && (!conf_b || out_conf_b), CSS_E_ARG, "css_cut_mix: a map without its output");
     CSS_CHECK_ARG(B > 0 && B <= 65535 && CH > 0 && H > 0 && H <= 65535 && W > 0, CSS_E_ARG, "css_cut_mix: bad size");
     CutMaps own{image, label_a, label_b, conf_a, conf_b}, par{p_image, p_label_a, p_label_b, p_conf_a, p_conf_b};
-    cut_mix_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, (cudaStream_t)stream>>>(own, par, boxes, (const unsigned long long*)class_sets,
+    css_launch(cut_mix_kernel, dim3(dim3((W + 255) / 256, H, B)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), own, par, boxes, (const unsigned long long*)class_sets,
                                                                                    mode, B, CH, H, W, out_image, out_label_a, out_label_b,
                                                                                    out_conf_a, out_conf_b);
     CSS_CHECK_LAUNCH("css_cut_mix", 1);

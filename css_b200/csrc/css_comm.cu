@@ -49,6 +49,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 __global__ void __launch_bounds__(COMM_THREADS) stats_allreduce_kernel(float* __restrict__ class_stats, void* local, void* const* __restrict__ peers,
                                                                        int rank, int world, int n, unsigned long long timeout_ns) {
+    css_pdl_enter();
     __shared__ unsigned int s_epoch;
     __shared__ int s_ok;
     __shared__ unsigned long long s_wait;
@@ -225,7 +226,7 @@ extern "C" int css_stats_allreduce(float* class_stats, void* local_buffer, void*
     CSS_CHECK_ARG(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world, CSS_E_ARG, "css_stats_allreduce: bad rank %d / world %d",
                   rank, world);
     if (int e = css_check_dims(C, D)) return e;
-    stats_allreduce_kernel<<<1, COMM_THREADS, 0, (cudaStream_t)stream>>>(class_stats, local_buffer, peer_buffers, rank, world, C * (D + 1),
+    css_launch(stats_allreduce_kernel, dim3(1), dim3(COMM_THREADS), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), class_stats, local_buffer, peer_buffers, rank, world, C * (D + 1),
                                                                          g_timeout_ms * 1000000ull);
     CSS_CHECK_LAUNCH("css_stats_allreduce", 1);
     return 0;

@@ -33,6 +33,7 @@ __device__ __forceinline__ void slab_apply(float* __restrict__ slab, const float
 __global__ void __launch_bounds__(GSL_THREADS, 4) grad_slab_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
                                                                    const float* __restrict__ grad_anchor, int n_anchor, int hw,
                                                                    int list_cap, float* __restrict__ grad_rep) {
+    css_pdl_enter();
     extern __shared__ __align__(16) float slab[];                  // [GSL_ELEMS] | list_a[list_cap] | list_s[list_cap]
     __shared__ int s_cnt;
     int* list_a = reinterpret_cast<int*>(slab + GSL_ELEMS);
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(GSL_THREADS, 4) grad_slab_kernel(const float* 
 __global__ void __launch_bounds__(CSS_D) grad_scatter_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
                                                              const float* __restrict__ grad_anchor, int n_anchor, int hw,
                                                              float* __restrict__ grad_rep) {
+    css_pdl_enter();
     const int base = blockIdx.x * GS_PER_BLOCK;
     int px[GS_PER_BLOCK];
     float g[GS_PER_BLOCK];
@@ -141,13 +143,13 @@ extern "C" int css_grad_scatter(const float* grad_out, const int32_t* anchor_px,
         int G = per_sm * css_sm_count() / B2;                       // all CTAs resident at once: no tail wave
         if (G > n_slabs) G = n_slabs;
         if (G < 1) G = 1;
-        grad_slab_kernel<<<dim3(G, B2), GSL_THREADS, smem, st>>>(grad_out, anchor_px, grad_anchor, n_anchor, h * w, list_cap, grad_rep);
+        css_launch(grad_slab_kernel, dim3(dim3(G, B2)), dim3(GSL_THREADS), (size_t)(smem), (cudaStream_t)(st), grad_out, anchor_px, grad_anchor, n_anchor, h * w, list_cap, grad_rep);
         CSS_CHECK_LAUNCH("css_grad_scatter", 1);
         return 0;
     }
     cudaError_t e = cudaMemsetAsync(grad_rep, 0, sizeof(float) * (size_t)total, st);
     if (e != cudaSuccess) { css_set_error("css_grad_scatter: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    grad_scatter_kernel<<<(n_anchor + GS_PER_BLOCK - 1) / GS_PER_BLOCK, CSS_D, 0, st>>>(grad_out, anchor_px, grad_anchor, n_anchor, h * w,
+    css_launch(grad_scatter_kernel, dim3((n_anchor + GS_PER_BLOCK - 1) / GS_PER_BLOCK), dim3(CSS_D), (size_t)(0), (cudaStream_t)(st), grad_out, anchor_px, grad_anchor, n_anchor, h * w,
                                                                                       grad_rep);
     CSS_CHECK_LAUNCH("css_grad_scatter", 1);
     return 0;

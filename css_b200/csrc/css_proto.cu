@@ -19,6 +19,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* scratch) {
 __global__ void __launch_bounds__(CSS_D) proto_ema_kernel(float* __restrict__ protos, const float* __restrict__ stats,
                                                           const int32_t* __restrict__ meta, float alpha, float one_minus_alpha,
                                                           int update_rule, float* __restrict__ proto_hat) {
+    css_pdl_enter();
     __shared__ float scratch[8];
     const int c = blockIdx.x, d = threadIdx.x;
     float p = protos[c * CSS_D + d];
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(CSS_D) proto_ema_kernel(float* __restrict__ pr
 // softmax(/temp) and its inclusive CDF (loss.py:133-135)
 __global__ void __launch_bounds__(CSS_D) class_cdf_kernel(const float* __restrict__ proto_hat, const int32_t* __restrict__ meta,
                                                           float temp, float* __restrict__ cdf) {
+    css_pdl_enter();
     __shared__ float sim[CSS_CMAX];
     const int k = blockIdx.x, d = threadIdx.x, warp = d >> 5, lane = d & 31;
     const int V = meta[CSS_META_V];
@@ -108,8 +110,8 @@ extern "C" int css_proto_ema(float* prototypes, const float* class_stats, const 
     CSS_CHECK_ARG(prototypes && class_stats && meta && proto_hat && class_cdf, CSS_E_ARG, "css_proto_ema: null pointer");
     CSS_CHECK_ARG(update_rule == CSS_UPDATE_LOCAL || update_rule == CSS_UPDATE_GLOBAL, CSS_E_ARG, "css_proto_ema: bad update_rule %d", update_rule);
     if (int e = css_check_dims(C, D)) return e;
-    proto_ema_kernel<<<C, CSS_D, 0, (cudaStream_t)stream>>>(prototypes, class_stats, meta, alpha, one_minus_alpha, update_rule, proto_hat);
-    class_cdf_kernel<<<CSS_CMAX, CSS_D, 0, (cudaStream_t)stream>>>(proto_hat, meta, temp, class_cdf);
+    css_launch(proto_ema_kernel, dim3(C), dim3(CSS_D), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), prototypes, class_stats, meta, alpha, one_minus_alpha, update_rule, proto_hat);
+    css_launch(class_cdf_kernel, dim3(CSS_CMAX), dim3(CSS_D), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), proto_hat, meta, temp, class_cdf);
     CSS_CHECK_LAUNCH("css_proto_ema", 2);
     return 0;
 }

@@ -91,6 +91,7 @@ __device__ __forceinline__ void build_slot_tables(SlotTables& t, const int32_t* 
 __global__ void __launch_bounds__(256) sample_kernel(const int32_t* __restrict__ meta, const float* __restrict__ class_cdf,
                                                      uint64_t seed, uint64_t offset, int Q, int Nn, int32_t* __restrict__ anchor_idx,
                                                      int32_t* __restrict__ neg_idx) {
+    css_pdl_enter();
     __shared__ SlotTables tb;
     const int k = blockIdx.y;
     const int V = meta[CSS_META_V];
@@ -123,7 +124,7 @@ extern "C" int css_sample(const int32_t* meta, const float* class_cdf, uint64_t 
     cudaMemsetAsync(neg_idx, 0xff, sizeof(int32_t) * (size_t)C * Q * Nn, st);
     const long long total = (long long)Q * (Nn + 1);
     dim3 grid((unsigned)min((total + 255) / 256, 4096ll), C);
-    sample_kernel<<<grid, 256, 0, st>>>(meta, class_cdf, seed, offset, Q, Nn, anchor_idx, neg_idx);
+    css_launch(sample_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)(st), meta, class_cdf, seed, offset, Q, Nn, anchor_idx, neg_idx);
     CSS_CHECK_LAUNCH("css_sample", 1);
     return 0;
 }
@@ -332,6 +333,7 @@ __device__ __forceinline__ void finish_query(Online& st, float z0, float cos_pos
 // publishes the Philox offset of this call, offset + *step_counter, into meta and bumps the device-resident counter so the
 // next call -- or the next replay of a captured CUDA graph -- draws fresh samples
 __global__ void draw_offset_kernel(uint64_t offset, unsigned long long* __restrict__ step_counter, int32_t* __restrict__ meta) {
+    css_pdl_enter();
     unsigned long long o = offset;
     if (step_counter) {
         o += *step_counter;
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
     uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
     float4* __restrict__ grad_anchor) {
+    css_pdl_enter();
     __shared__ SlotTables tb;
     __shared__ QueryShared sh;
     const int k = blockIdx.y, q = blockIdx.x;
@@ -483,6 +486,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_kq, const int32_t* __restrict__ meta, int Q,
                                                           float* __restrict__ loss) {
+    css_pdl_enter();
     __shared__ float part[8];
     const int V = meta[CSS_META_V];
     float s = 0.f;
@@ -518,7 +522,7 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
     CSS_CHECK_ARG(Q <= 65535 * 32768, CSS_E_SIZE, "css_score_ce: Q too large");
     if (int e = css_check_dims(C, D)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    draw_offset_kernel<<<1, 1, 0, st>>>(offset, (unsigned long long*)step_counter, meta);
+    css_launch(draw_offset_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)(st), offset, (unsigned long long*)step_counter, meta);
     dim3 grid(Q, C);
     // fixed-reference softmax whenever 2^(-2 log2(e)/temp) is far from fp32 underflow (temp > ~0.024); online max otherwise
     const bool fix = (2.f * 1.4426950408889634f / temp) < 120.f;
@@ -527,8 +531,8 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
 #define SC_RUN(RT_)                                                                                                 \
     do {                                                                                                            \
         if (grad_anchor) {                                                                                          \
-            if (fix) score_ce_kernel<true, false, true, true, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));         \
-            else score_ce_kernel<true, false, true, false, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));           \
+            if (fix) css_launch(score_ce_kernel<true, false, true, true, RT_>, dim3(grid), dim3(SC_THREADS), (size_t)(0), (cudaStream_t)(st), SC_ARGS(RT_));         \
+            else css_launch(score_ce_kernel<true, false, true, false, RT_>, dim3(grid), dim3(SC_THREADS), (size_t)(0), (cudaStream_t)(st), SC_ARGS(RT_));           \
         } else {                                                                                                    \
             if (fix) score_ce_kernel<false, sizeof(RT_) == 4, false, true, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));       \
             else score_ce_kernel<false, sizeof(RT_) == 4, false, false, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));         \
@@ -538,7 +542,7 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
     else SC_RUN(__nv_bfloat16);
 #undef SC_RUN
 #undef SC_ARGS
-    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_kq, meta, Q, loss);
+    css_launch(loss_reduce_kernel, dim3(1), dim3(256), (size_t)(0), (cudaStream_t)(st), loss_kq, meta, Q, loss);
     CSS_CHECK_LAUNCH("css_score_ce", 3);
     return 0;
 }

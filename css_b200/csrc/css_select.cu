@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const flo
                                                                        int N, int T, uint32_t* __restrict__ valid_bits,
                                                                        uint32_t* __restrict__ hard_bits, int32_t* __restrict__ tile_counts,
                                                                        int32_t* __restrict__ meta) {
+    css_pdl_enter();
     __shared__ int cnt[2 * CSS_CMAX];
     if (threadIdx.x < 2 * CSS_CMAX) cnt[threadIdx.x] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(CSS_SEL_TILE) select_classify_kernel(const flo
 #define SCAN_THREADS 256
 #define SCAN_MAXSEG 16
 __global__ void __launch_bounds__(SCAN_THREADS) select_scan_kernel(int32_t* __restrict__ tile_counts, int C, int T, int32_t* __restrict__ meta) {
+    css_pdl_enter();
     __shared__ int wsum[SCAN_THREADS / 32];
     __shared__ int is_last;
     const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) select_scan_kernel(int32_t* __re
 __global__ void __launch_bounds__(CSS_SEL_TILE) select_scatter_kernel(const uint32_t* __restrict__ valid_bits, const uint32_t* __restrict__ hard_bits,
                                                                       const int32_t* __restrict__ tile_off, int C, int N, int T,
                                                                       int32_t* __restrict__ valid_list, int32_t* __restrict__ hard_list) {
+    css_pdl_enter();
     __shared__ int wcnt[2][CSS_CMAX][CSS_SEL_TILE / 32];
     __shared__ int toff[2 * CSS_CMAX];             // this tile's offsets of all 2C lists: one round trip, not one per class
     for (int i = threadIdx.x; i < 2 * CSS_CMAX * (CSS_SEL_TILE / 32); i += CSS_SEL_TILE) (&wcnt[0][0][0])[i] = 0;
@@ -199,10 +202,10 @@ extern "C" int css_select(const float* label, const float* mask, const float* pr
     CSS_CHECK_ARG((long long)B2 * h * w * CSS_CMAX < (1ll << 31), CSS_E_SIZE, "css_select: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w, N = B2 * hw, T = css_select_tiles(N);
-    select_classify_kernel<<<T, CSS_SEL_TILE, 0, st>>>(label, mask, prob, strong_threshold, C, hw, N, T, valid_bits, hard_bits,
+    css_launch(select_classify_kernel, dim3(T), dim3(CSS_SEL_TILE), (size_t)(0), (cudaStream_t)(st), label, mask, prob, strong_threshold, C, hw, N, T, valid_bits, hard_bits,
                                                       tile_counts, meta);
-    select_scan_kernel<<<2 * C, SCAN_THREADS, 0, st>>>(tile_counts, C, T, meta);
-    select_scatter_kernel<<<T, CSS_SEL_TILE, 0, st>>>(valid_bits, hard_bits, tile_counts, C, N, T, valid_list, hard_list);
+    css_launch(select_scan_kernel, dim3(2 * C), dim3(SCAN_THREADS), (size_t)(0), (cudaStream_t)(st), tile_counts, C, T, meta);
+    css_launch(select_scatter_kernel, dim3(T), dim3(CSS_SEL_TILE), (size_t)(0), (cudaStream_t)(st), valid_bits, hard_bits, tile_counts, C, N, T, valid_list, hard_list);
     CSS_CHECK_LAUNCH("css_select", 3);
     return 0;
 }
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256) threshold_glue_kernel(const int64_t* __re
                                                              const float* __restrict__ conf_u, float weak, int mode, int B, int C,
                                                              int H, int W, int h, int w, float sy, float sx,
                                                              float* __restrict__ label_all, float* __restrict__ mask_all) {
+    css_pdl_enter();
     const int hw = h * w;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 2 * B * hw) return;
@@ -251,7 +255,7 @@ extern "C" int css_threshold_glue(const int64_t* label_l, const int64_t* label_u
     CSS_CHECK_ARG(C >= 1 && C <= CSS_CMAX, CSS_E_DIM, "css_threshold_glue: C must be in [1,%d]", CSS_CMAX);
     CSS_CHECK_ARG(2ll * B * h * w * CSS_CMAX < (1ll << 31), CSS_E_SIZE, "css_threshold_glue: too many pixels");
     const int n = 2 * B * h * w;
-    threshold_glue_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(label_l, label_u, conf_u, weak_threshold, mode, B, C,
+    css_launch(threshold_glue_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), label_l, label_u, conf_u, weak_threshold, mode, B, C,
                                                                             H, W, h, w, (float)H / (float)h, (float)W / (float)w,
                                                                             label_all, mask_all);
     CSS_CHECK_LAUNCH("css_threshold_glue", 1);

@@ -15,6 +15,7 @@ bool css_rep_pass_use_tc();
 // (class-minor, zero padded) so the streaming kernel reads 4 classes per 128-bit shared-memory load.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CSS_D) proto_prep_kernel(const float* __restrict__ protos, float* __restrict__ scratch, int C) {
+    css_pdl_enter();
     __shared__ float part[CSS_D / 32];
     const int c = blockIdx.x, d = threadIdx.x;
     if (c >= C) {                                   // padding columns
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
                                                                          int hw, int N, int C, int mode, float temp,
                                                                          float* __restrict__ out, T* __restrict__ rows,
                                                                          float* __restrict__ norms, const int32_t* __restrict__ guard) {
+    css_pdl_enter();
     if (guard != nullptr && *guard == 0) return;     // css_rows_refresh: the carried rows were verified, nothing to redo
     constexpr int DS = CSS_D / SM_KS;          // channels per slice
     constexpr int PL = 32 / SM_KS;             // pixel lanes per warp
@@ -240,7 +242,7 @@ static void launch_rep_pass(const T* rep, const float* scratch, int hw, int N, i
     constexpr int WP = (32 / SM_KS) * SM_PPT;
     const int n_blocks = ((N + WP - 1) / WP + SM_WARPS - 1) / SM_WARPS;
     const int cap = css_cached_sm_count() * SM_MINB;
-    rep_pass_kernel<NG, ROWS, T, T1><<<n_blocks < cap ? n_blocks : cap, SM_WARPS * 32, 0, st>>>(rep, scratch, hw, N, C, mode, temp, out,
+    css_launch(rep_pass_kernel<NG, ROWS, T, T1>, dim3(n_blocks < cap ? n_blocks : cap), dim3(SM_WARPS * 32), (size_t)0, st, rep, scratch, hw, N, C, mode, temp, out,
                                                                                             rows, norms, guard);
 }
 
@@ -301,7 +303,7 @@ extern "C" int css_rep_pass(const void* rep, int rep_dtype, const float* prototy
         return 0;
     }
     if (want_sim) {
-        proto_prep_kernel<<<CSS_CMAX, CSS_D, 0, st>>>(prototypes, proto_scratch, C);
+        css_launch(proto_prep_kernel, dim3(CSS_CMAX), dim3(CSS_D), (size_t)(0), (cudaStream_t)(st), prototypes, proto_scratch, C);
         ++launches;
     }
 #define REP_PASS_RUN(TYPE)                                                                                                  \
@@ -338,6 +340,7 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
 template <typename T>
 __global__ void __launch_bounds__(256) rows_verify_kernel(const T* __restrict__ rep, const T* __restrict__ rows, int hw, int N,
                                                           int32_t* __restrict__ meta) {
+    css_pdl_enter();
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p >= N) return;
     const int b = p / hw, s = p - b * hw;
@@ -366,10 +369,10 @@ extern "C" int css_rows_refresh(const void* rep, int rep_dtype, void* rows, floa
     const int hw = h * w, N = B * hw;
     const int32_t* guard = meta + CSS_META_ROWS_STALE;
     if (rep_dtype == CSS_DTYPE_F32) {
-        rows_verify_kernel<float><<<(N + 255) / 256, 256, 0, st>>>((const float*)rep, (const float*)rows, hw, N, meta);
+        css_launch(rows_verify_kernel<float>, dim3((N + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)(st), (const float*)rep, (const float*)rows, hw, N, meta);
         launch_rep_pass<0, true, float>((const float*)rep, nullptr, hw, N, 1, CSS_SIM_COS, 1.f, nullptr, (float*)rows, norms, st, guard);
     } else {
-        rows_verify_kernel<__nv_bfloat16><<<(N + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)rep, (const __nv_bfloat16*)rows, hw, N, meta);
+        css_launch(rows_verify_kernel<__nv_bfloat16>, dim3((N + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)(st), (const __nv_bfloat16*)rep, (const __nv_bfloat16*)rows, hw, N, meta);
         launch_rep_pass<0, true, __nv_bfloat16>((const __nv_bfloat16*)rep, nullptr, hw, N, 1, CSS_SIM_COS, 1.f, nullptr,
                                                 (__nv_bfloat16*)rows, norms, st, guard);
     }
@@ -504,6 +507,7 @@ __global__ void __launch_bounds__(K2_TH * K2_TW, STAGED ? 5 : 1) upsample_label_
     const float* __restrict__ sim, const float* __restrict__ logits, float temp, float rtemp, int tmode, int fuse_mode, int C, int h, int w, int H, int W,
     float ry, float rx, int tile_cap, float* __restrict__ conf_rep, int64_t* __restrict__ label_rep, float* __restrict__ conf_cls,
     int64_t* __restrict__ label_cls, float* __restrict__ fused) {
+    css_pdl_enter();
     extern __shared__ __align__(16) float tile[];   // [2 maps][tile_cap positions][CP classes]  (STAGED only)
     const int b = blockIdx.z;
     const int Y0 = blockIdx.y * K2_TH, X0 = blockIdx.x * K2_TW;
@@ -602,7 +606,7 @@ extern "C" int css_upsample_label_fuse(const float* sim, const float* logits, fl
     const int tmode = (frexpf(temp, &texp) == 0.5f) ? 1 : 2;
     const float rtemp = 1.f / temp;
 #define K2_LAUNCH(STG, CTV, SM)                                                                                                     \
-    upsample_label_fuse_kernel<STG, CTV><<<grid, K2_TH * K2_TW, SM, st>>>(sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, \
+    css_launch(upsample_label_fuse_kernel<STG, CTV>, dim3(grid), dim3(K2_TH * K2_TW), (size_t)(SM), (cudaStream_t)(st), sim, logits, temp, rtemp, tmode, fuse_mode, C, h, w, H, W, ry, \
                                                                          rx, tile_cap, conf_rep, label_rep, conf_cls, label_cls, fused)
     if (smem <= 96 * 1024) {
         if (smem > 48 * 1024) {

@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 
 // F.normalize(prototypes, dim=-1) (eps 1e-12, ddp_model.py:107) split into TF32 hi / lo parts, written in the shared-memory image
 __global__ void __launch_bounds__(CSS_D) proto_prep_tc_kernel(const float* __restrict__ protos, char* __restrict__ image, int C) {
+    css_pdl_enter();
     __shared__ float part[CSS_D / 32];
     const int c = blockIdx.x, d = threadIdx.x;
     float v = 0.f;
@@ -186,6 +187,7 @@ template <bool ROWS, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_tc_kernel(const float* __restrict__ rep, const char* __restrict__ b_image, int hw,
                                                                     int n_img, int C, int mode, float temp, float* __restrict__ out,
                                                                     float* __restrict__ rows, float* __restrict__ norms) {
+    css_pdl_enter();
     extern __shared__ char smem_raw[];
     char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms: 1 KB aligned
     char* sB = smem;                                        // [hi 32 KB | lo 32 KB]
@@ -435,7 +437,7 @@ int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scra
                     float* sim_out, float* rows, float* norms, cudaStream_t st) {
     const int hw = h * w;
     char* image = reinterpret_cast<char*>(proto_scratch);
-    proto_prep_tc_kernel<<<TC_N, CSS_D, 0, st>>>(prototypes, image, C);
+    css_launch(proto_prep_tc_kernel, dim3(TC_N), dim3(CSS_D), (size_t)(0), (cudaStream_t)(st), prototypes, image, C);
     const int n_tiles = B * ((hw + TC_M - 1) / TC_M);
     const int sms = css_cached_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
@@ -444,7 +446,7 @@ int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scra
     do {                                                                                                                              \
         e = cudaFuncSetAttribute(rep_pass_tc_kernel<ROWS_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);          \
         if (e == cudaSuccess)                                                                                                         \
-            rep_pass_tc_kernel<ROWS_, NP_><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(rep, image, hw, B, C, mode, temp, sim_out, rows, norms); \
+            css_launch(rep_pass_tc_kernel<ROWS_, NP_>, dim3(grid), dim3(TC_THREADS), (size_t)(TC_SMEM_BYTES), (cudaStream_t)(st), rep, image, hw, B, C, mode, temp, sim_out, rows, norms); \
     } while (0)
     if (rows) {
         if (C <= 24) TC_LAUNCH(true, 3);

@@ -38,6 +38,7 @@ template <typename RT>
 __global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const RT* __restrict__ rows, const uint32_t* __restrict__ valid_bits,
                                                                 int C, int N, float4* __restrict__ partials,
                                                                 uint32_t* __restrict__ touched) {
+    css_pdl_enter();
     const int t = threadIdx.x;
     const int p_begin = (int)(((long long)N * blockIdx.x) / gridDim.x);
     const int p_end = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(CS_THREADS) class_sums_kernel(const RT* __rest
 __global__ void __launch_bounds__(CR_DCH * CR_SEG) class_reduce_kernel(const float* __restrict__ partials, const uint32_t* __restrict__ touched,
                                                                        const int32_t* __restrict__ meta, int G, int C,
                                                                        float* __restrict__ class_stats) {
+    css_pdl_enter();
     extern __shared__ int glist[];                 // [G]
     __shared__ int wtot[CR_DCH * CR_SEG / 32];
     __shared__ float segsum[CR_SEG][CR_DCH];
@@ -147,10 +149,10 @@ extern "C" int css_class_stats(const void* rows, int rows_dtype, const uint32_t*
     const int G = css_class_blocks(N);
     CSS_CHECK_ARG(rows_dtype == CSS_DTYPE_F32 || rows_dtype == CSS_DTYPE_BF16, CSS_E_DTYPE, "css_class_stats: rows dtype %d", rows_dtype);
     if (rows_dtype == CSS_DTYPE_F32)
-        class_sums_kernel<float><<<G, CS_THREADS, 0, st>>>((const float*)rows, valid_bits, C, N, (float4*)partials, touched);
+        css_launch(class_sums_kernel<float>, dim3(G), dim3(CS_THREADS), (size_t)(0), (cudaStream_t)(st), (const float*)rows, valid_bits, C, N, (float4*)partials, touched);
     else
-        class_sums_kernel<__nv_bfloat16><<<G, CS_THREADS, 0, st>>>((const __nv_bfloat16*)rows, valid_bits, C, N, (float4*)partials, touched);
-    class_reduce_kernel<<<dim3(C, CSS_D / CR_DCH), CR_DCH * CR_SEG, G * sizeof(int), st>>>(partials, touched, meta, G, C, class_stats);
+        css_launch(class_sums_kernel<__nv_bfloat16>, dim3(G), dim3(CS_THREADS), (size_t)(0), (cudaStream_t)(st), (const __nv_bfloat16*)rows, valid_bits, C, N, (float4*)partials, touched);
+    css_launch(class_reduce_kernel, dim3(dim3(C, CSS_D / CR_DCH)), dim3(CR_DCH * CR_SEG), (size_t)(G * sizeof(int)), (cudaStream_t)(st), partials, touched, meta, G, C, class_stats);
     CSS_CHECK_LAUNCH("css_class_stats", 2);
     return 0;
 }
