@@ -30,6 +30,10 @@ WORKLOADS = {
     "voc321_ori": dict(B=8, C=21, h=81, w=81, H=321, W=321, Q=256, Nn=512, temp=0.5, strong=0.97, weak=0.7, strategy="ori"),
     # BASELINE.json configs[3]: CityScapes, 768x768 crops, deep-stem rep 193x193, 19 classes, B=4 per GPU (YAML)
     "city768_cross": dict(B=4, C=19, h=193, w=193, H=769, W=769, Q=256, Nn=512, temp=0.5, strong=0.8, weak=0.7, strategy="cross"),
+    # extension: the same VOC step on CHANNELS-LAST representation maps (model.to(memory_format=torch.channels_last)):
+    # the map is its own pixel-major row table, TMA + tcgen05 similarity pass, no transposing copy.  Not a BASELINE configuration.
+    "voc321_mix_nhwc": dict(B=8, C=21, h=81, w=81, H=321, W=321, Q=256, Nn=512, temp=0.5, strong=0.8, weak=0.7, strategy="mix", layout="nhwc"),
+    "city768_cross_nhwc": dict(B=4, C=19, h=193, w=193, H=769, W=769, Q=256, Nn=512, temp=0.5, strong=0.8, weak=0.7, strategy="cross", layout="nhwc"),
     # BASELINE.json configs[0]: the reference's own CPU-runnable case (loss only)
     "voc81_b1_loss": dict(B=1, C=21, h=81, w=81, H=321, W=321, Q=256, Nn=512, temp=0.5, strong=0.97, weak=0.7, strategy="ori"),
 }
@@ -322,7 +326,8 @@ def reference_arm(args, cfg):
 def workload_config(args, cfg):
     return {"workload": f"{args.workload}: {cfg['strategy']} strategy, B={cfg['B']}/GPU, C={cfg['C']}, rep {cfg['h']}x{cfg['w']}x{D} "
                         f"-> crop {cfg['H']}x{cfg['W']}, Q={cfg['Q']}, Nn={cfg['Nn']}, temp={cfg['temp']}, strong={cfg['strong']} "
-                        "(BASELINE configs[1] shape; four-stage path incl. rep-space label + fusion of configs[2])",
+                        + ("(channels-last representation maps: extension, not a BASELINE configuration)" if cfg.get("layout") == "nhwc" else
+                           "(BASELINE configs[1] shape; four-stage path incl. rep-space label + fusion of configs[2])"),
             "pixels_per_step_per_gpu": 2 * cfg["B"] * cfg["h"] * cfg["w"],
             "parallelism": f"batch-sharded x{args.gpus}, one sum of the [C,D+1] class sums|counts block per step",
             "l2": "no explicit flush: per-step working set (rep_u + rep_all + pixel-major copy + grad_rep ~ 400 MB) exceeds the 126 MB L2"}
@@ -397,6 +402,9 @@ def main():
     temp, strategy = cfg["temp"], cfg["strategy"]
     N = 2 * B * h * w
     host = make_inputs(cfg, rank)
+    if cfg.get("layout") == "nhwc":              # what a channels_last network hands over: same values, [pixel][channel] memory
+        for k in ("rep_u", "rep_all"):
+            host[k] = host[k].contiguous(memory_format=torch.channels_last)
     gpu = {k: v.to(dev) for k, v in host.items()}
     protos = gpu["prototypes"].clone()
     crit = css_b200.Contrast_Loss(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=cfg["strong"], alpha=0.99,
@@ -591,7 +599,7 @@ def main():
     # ---- e2e: host buffers, H2D of every input + D2H of the loss and of the maps the augmentation receives -----------------
     keys = ["rep_u", "pred_u", "rep_all", "label", "mask"] if strategy != "ori" else ["pred_u", "rep_all", "label", "mask", "prob_ori"]
     numa = pin_to_gpu_numa_node(physical_gpu_index(local_rank))          # before the pinned buffers are allocated (first touch)
-    pinned = {k: host[k].clone().pin_memory() for k in keys}
+    pinned = {k: host[k].clone(memory_format=torch.preserve_format).pin_memory() for k in keys}
     unpin_cpu()
     # two staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i; every step still uploads all
     # of its inputs from pinned host memory and reads its loss and label / confidence maps back
@@ -714,10 +722,13 @@ def main():
     if rep_ms.get("student"):
         t_st = rep_ms["student"]
         s_el = 4
-        alg = N * (D * s_el + 4 * C + D * s_el + 4)
+        nhwc = cfg.get("layout") == "nhwc"
+        alg = N * (D * s_el + 4 * C + 4) if nhwc else N * (D * s_el + 4 * C + D * s_el + 4)
         tr = prof.get("rep_pass_student")
-        roofline_hbm = {"bound": "hbm", "kernel": "rep_pass_kernel<SOFTMAX, rows> (css_rep_pass, student: one read of rep_all -> prob_all + pixel-major "
-                        "rows + norms; timed with the prototype-preparation launch of the same call)", "achieved": alg / (t_st * 1e-3) / 1e9, "peak": peak,
+        roofline_hbm = {"bound": "hbm", "kernel": ("rep_pass_nhwc_kernel (css_rep_pass_nhwc, student: one TMA read of the channels-last rep_all -> prob_all + "
+                                   "norms, tcgen05 / TMEM; timed with the prototype-preparation launch of the same call)") if nhwc else
+                        ("rep_pass_kernel<SOFTMAX, rows> (css_rep_pass, student: one read of rep_all -> prob_all + pixel-major "
+                         "rows + norms; timed with the prototype-preparation launch of the same call)"), "achieved": alg / (t_st * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg / (t_st * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": tr,
                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_st, "share_of_step": t_st / ms_per_step,
                         "dram_frac_of_hbm": (tr / (t_st * 1e-3) / 1e9 / peak) if tr else None,

@@ -154,3 +154,39 @@ extern "C" int css_grad_scatter(const float* grad_out, const int32_t* anchor_px,
     CSS_CHECK_LAUNCH("css_grad_scatter", 1);
     return 0;
 }
+
+
+// -------------------------------------------------------------------------------------------------------------------
+// Channels-last gradient: grad_rep's memory is [pixel][256], so the dense gradient is a linear zero fill plus one 1 KB row
+// update per anchor (duplicates accumulate with red.global.add).
+// -------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CSS_D) grad_rows_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ anchor_px,
+                                                          const float* __restrict__ grad_anchor, int n_anchor, float* __restrict__ grad_rows) {
+    css_pdl_enter();
+    const int base = blockIdx.x * GS_PER_BLOCK;
+    int px[GS_PER_BLOCK];
+    float g[GS_PER_BLOCK];
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i) px[i] = (base + i < n_anchor) ? __ldg(anchor_px + base + i) : -1;
+    const float go = __ldg(grad_out);
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i)
+        g[i] = (px[i] >= 0) ? ldg_stream(grad_anchor + (size_t)(base + i) * CSS_D + threadIdx.x) : 0.f;
+#pragma unroll
+    for (int i = 0; i < GS_PER_BLOCK; ++i)
+        if (px[i] >= 0) atomicAdd(grad_rows + (size_t)px[i] * CSS_D + threadIdx.x, go * g[i]);
+}
+
+extern "C" int css_grad_scatter_nhwc(const float* grad_out, const int32_t* anchor_px, const float* grad_anchor, int n_anchor, int B2, int D,
+                                     int h, int w, float* grad_rows, void* stream) {
+    CSS_CHECK_ARG(grad_out && anchor_px && grad_anchor && grad_rows, CSS_E_ARG, "css_grad_scatter_nhwc: null pointer");
+    CSS_CHECK_ARG(n_anchor > 0 && B2 > 0 && h > 0 && w > 0, CSS_E_ARG, "css_grad_scatter_nhwc: non-positive size");
+    CSS_CHECK_ARG(D == CSS_D, CSS_E_DIM, "css_grad_scatter_nhwc: D must be %d", CSS_D);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_rows, 0, sizeof(float) * (size_t)B2 * D * h * w, st);
+    if (e != cudaSuccess) { css_set_error("css_grad_scatter_nhwc: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    css_launch(grad_rows_kernel, dim3((n_anchor + GS_PER_BLOCK - 1) / GS_PER_BLOCK), dim3(CSS_D), (size_t)0, st, grad_out, anchor_px, grad_anchor, n_anchor,
+               grad_rows);
+    CSS_CHECK_LAUNCH("css_grad_scatter_nhwc", 1);
+    return 0;
+}

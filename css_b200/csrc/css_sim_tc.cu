@@ -33,6 +33,9 @@
 //     "empty" barrier; the accumulators are double-buffered in TMEM (2 x 160 columns), so the next tile's MMAs run while
 //   * four epilogue warps (lane = TMEM lane = pixel) read the previous tile: tcgen05.ld of the five accumulators,
 //     1 / max(||x||, 1e-12), optional softmax, coalesced NCHW stores, norms.
+#include <stdlib.h>
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "css_common.cuh"
 
 #define TC_PRODUCERS 512               // 16 producer warps
@@ -460,5 +463,349 @@ int css_rep_pass_tc(const float* rep, const float* prototypes, float* proto_scra
         css_set_error("css_rep_pass (tensor-core path): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
     }
+    return 0;
+}
+
+
+// =====================================================================================================================
+// Channels-last maps (torch.channels_last: memory is [pixel][256], i.e. the map IS the pixel-major row table of the loss)
+// =====================================================================================================================
+// With rows contiguous and 1 KB aligned the pass needs no transposition and no copy at all:
+//   * one thread issues a 2-D TMA tensor copy per 32-channel chunk ([128 rows x 32 channels] box, SWIZZLE_128B): the tile lands in
+//     shared memory in exactly the K-major layout the tensor core reads, NL_RAW chunks in flight per CTA;
+//   * the tensor core TRUNCATES an fp32 bit pattern to TF32 (tools/dev/dev_umma.cu), so the raw tile is the "hi" operand as it
+//     is; 16 producer warps only compute lo = x - trunc_tf32(x) (exact) into a second tile at the same swizzled positions, and
+//     the norm partials;
+//   * MMA warp / TMEM accumulators / epilogue as in the NCHW kernel above.  Output: sim / prob [B,C,h,w] and ||x_p||.
+#define NL_RAW 6                                  // raw chunks in flight per CTA (16 KB each)
+#define NL_LO 2                                   // lo stages
+#define NL_SMEM_BYTES (2 * TC_B_HALF + NL_RAW * TC_STAGE_HALF + NL_LO * TC_STAGE_HALF + 4096 + 1024)
+
+struct NlShared {
+    unsigned long long raw_full[NL_RAW];    // TMA -> producers, MMA warp: the raw chunk has landed          (1 arrival + transaction bytes)
+    unsigned long long raw_empty[NL_RAW];   // producers (16 warp arrivals) + MMA warp (tcgen05.commit) -> TMA thread: slot is free
+    unsigned long long lo_full[NL_LO];      // producers -> MMA warp: the lo tile is written                  (16 warp arrivals)
+    unsigned long long lo_empty[NL_LO];     // MMA warp -> producers: the MMAs that read the lo tile are done (tcgen05.commit)
+    unsigned long long acc_full[2];
+    unsigned long long acc_empty[2];
+    unsigned long long n2_full[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    float n2[2][4][TC_M];
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(TC_THREADS, 1) rep_pass_nhwc_kernel(const __grid_constant__ CUtensorMap tmap, const char* __restrict__ b_image,
+                                                                      int hw, int N, int C, int mode, float temp, float* __restrict__ out,
+                                                                      float* __restrict__ norms, const int32_t* __restrict__ guard, int dbg) {
+    css_pdl_enter();
+    if (guard != nullptr && *guard == 0) return;            // css_rows_refresh_nhwc: the carried norms were verified, nothing to redo
+    extern __shared__ char smem_raw[];
+    char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    char* sB = smem;                                        // [hi 32 KB | lo 32 KB]
+    char* sR = smem + 2 * TC_B_HALF;                        // raw ring: slot r at r * 16 KB, K-major SWIZZLE_128B (written by TMA)
+    char* sL = sR + NL_RAW * TC_STAGE_HALF;                 // lo stages
+    NlShared* sh = reinterpret_cast<NlShared*>(sL + NL_LO * TC_STAGE_HALF);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int MMA_WARP = TC_PRODUCERS / 32 + 4, LOAD_WARP = MMA_WARP + 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < NL_RAW; ++i) {
+            mbar_init(smem_u32(&sh->raw_full[i]), 1);
+            mbar_init(smem_u32(&sh->raw_empty[i]), TC_PRODUCERS / 32 + 1);
+        }
+        for (int i = 0; i < NL_LO; ++i) {
+            mbar_init(smem_u32(&sh->lo_full[i]), TC_PRODUCERS / 32);
+            mbar_init(smem_u32(&sh->lo_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&sh->acc_full[i]), 1);
+            mbar_init(smem_u32(&sh->acc_empty[i]), 4);
+            mbar_init(smem_u32(&sh->n2_full[i]), TC_PRODUCERS / 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(b_image);
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (int i = tid; i < 2 * TC_B_HALF / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sh->tmem_base;
+    const int n_tiles = (N + TC_M - 1) / TC_M;
+
+    if (warp == LOAD_WARP) {
+        // =========================================== TMA issuer ===========================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                    const uint32_t rslot = g % NL_RAW, use = g / NL_RAW;
+                    if (use > 0) mbar_wait(smem_u32(&sh->raw_empty[rslot]), (use - 1u) & 1u);
+                    const uint32_t bar = smem_u32(&sh->raw_full[rslot]);
+                    mbar_arrive_expect_tx(bar, TC_STAGE_HALF);                   // rows past the end of the map are zero-filled
+                    tma_load_2d(smem_u32(sR) + rslot * TC_STAGE_HALF, &tmap, ch * TC_KC, tile * TC_M, bar);
+                }
+            }
+        }
+    } else if (warp < TC_PRODUCERS / 32) {
+        // =========================================== producers: lo tile + norm partials ===========================================
+        const int pg = warp & 3, co = warp >> 2;
+        const int m = pg * 32 + lane;
+        const uint32_t a_row = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+        const uint32_t off0 = (uint32_t)(((2 * co) ^ (m & 7)) << 4), off1 = (uint32_t)(((2 * co + 1) ^ (m & 7)) << 4);
+        uint32_t g = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            float n2 = 0.f;
+            for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                const uint32_t rslot = g % NL_RAW, slot = g % NL_LO, use = g / NL_LO;
+                mbar_wait(smem_u32(&sh->raw_full[rslot]), (g / NL_RAW) & 1u);
+                const char* rp = sR + rslot * TC_STAGE_HALF + a_row;
+                const uint4 q0 = *reinterpret_cast<const uint4*>(rp + off0), q1 = *reinterpret_cast<const uint4*>(rp + off1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh->raw_empty[rslot]));       // (the MMA warp's commit is the 17th arrival)
+                const uint32_t xs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                uint32_t lo[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float x = __uint_as_float(xs[u]);
+                    lo[u] = __float_as_uint(__fsub_rn(x, __uint_as_float(xs[u] & 0xFFFFE000u)));      // exact: x - trunc_tf32(x)
+                    n2 = fmaf(x, x, n2);
+                }
+                if (use > 0) mbar_wait(smem_u32(&sh->lo_empty[slot]), (use - 1u) & 1u);
+                char* lp = sL + slot * TC_STAGE_HALF + a_row;
+                *reinterpret_cast<uint4*>(lp + off0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(lp + off1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                if (ch == TC_NCHUNK - 1) sh->n2[tile_it & 1u][co][m] = n2;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&sh->lo_full[slot]));
+                    if (ch == TC_NCHUNK - 1) mbar_arrive(smem_u32(&sh->n2_full[tile_it & 1u]));
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================== MMA issuer ===========================================
+        const uint32_t sR_u = smem_u32(sR), sL_u = smem_u32(sL), sB_u = smem_u32(sB);
+        uint32_t g = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t buf = tile_it & 1u, d_base = tmem + buf * TC_ACC_COLS;
+            if (tile_it >= 2) mbar_wait(smem_u32(&sh->acc_empty[buf]), ((tile_it >> 1) - 1u) & 1u);
+            tc_fence_after();
+            for (int ch = 0; ch < TC_NCHUNK; ++ch, ++g) {
+                const uint32_t rslot = g % NL_RAW, slot = g % NL_LO;
+                mbar_wait(smem_u32(&sh->raw_full[rslot]), (g / NL_RAW) & 1u);
+                mbar_wait(smem_u32(&sh->lo_full[slot]), (g / NL_LO) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = sR_u + rslot * TC_STAGE_HALF, a_lo = sL_u + slot * TC_STAGE_HALF;
+                    const uint32_t b_blk = (uint32_t)ch * 4096;
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        const uint64_t da_hi = umma_desc(a_hi + ks * 32, 16, 1024), da_lo = umma_desc(a_lo + ks * 32, 16, 1024);
+                        const uint64_t db_hi = umma_desc(sB_u + b_blk + ks * 32, 16, 1024), db_lo = umma_desc(sB_u + TC_B_HALF + b_blk + ks * 32, 16, 1024);
+                        if (!(dbg & 1)) umma_tf32(d_base + (ch >> 1) * TC_N, da_hi, db_hi, ((ch & 1) | ks) != 0);
+                        if (!(dbg & 3)) umma_tf32(d_base + TC_NACC * TC_N, da_lo, db_hi, (ch | ks) != 0);
+                        if (!(dbg & 3)) umma_tf32(d_base + TC_NACC * TC_N, da_hi, db_lo, 1);
+                    }
+                    umma_commit(smem_u32(&sh->raw_empty[rslot]));
+                    umma_commit(smem_u32(&sh->lo_empty[slot]));
+                    if (ch == TC_NCHUNK - 1) umma_commit(smem_u32(&sh->acc_full[buf]));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================================== epilogue ===========================================
+        const int pg = warp & 3;
+        const int m = pg * 32 + lane;
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t buf = tile_it & 1u, par = (tile_it >> 1) & 1u;
+            const int pix = tile * TC_M + m;
+            mbar_wait(smem_u32(&sh->n2_full[buf]), par);
+            const float* n2p = &sh->n2[buf][0][m];
+            const float n2 = (n2p[0] + n2p[TC_M]) + (n2p[2 * TC_M] + n2p[3 * TC_M]);
+            mbar_wait(smem_u32(&sh->acc_full[buf]), par);
+            tc_fence_after();
+            float val[NP * 8];
+            const uint32_t t_lane = tmem + buf * TC_ACC_COLS + ((uint32_t)(pg * 32) << 16);
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                float a0[8], a1[8], s01[8];
+                tmem_ld8(t_lane + 0 * TC_N + part * 8, a0);
+                tmem_ld8(t_lane + 1 * TC_N + part * 8, a1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s01[i] = a0[i] + a1[i];
+                tmem_ld8(t_lane + 2 * TC_N + part * 8, a0);
+                tmem_ld8(t_lane + 3 * TC_N + part * 8, a1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s01[i] += a0[i] + a1[i];
+                tmem_ld8(t_lane + 4 * TC_N + part * 8, a0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) val[part * 8 + i] = s01[i] + a0[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sh->acc_empty[buf]));
+            if (pix < N) {
+                const float nrm_raw = sqrtf(n2);
+                if (norms) norms[pix] = nrm_raw;
+                if (out) {
+                    const float inv = __frcp_rn(fmaxf(nrm_raw, 1e-12f));
+#pragma unroll
+                    for (int c = 0; c < NP * 8; ++c) val[c] *= inv;
+                    if (mode == CSS_SIM_SOFTMAX) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int c = 0; c < NP * 8; ++c)
+                            if (c < C) mx = fmaxf(mx, val[c]);
+                        const float k2 = 1.4426950408889634f / temp;
+                        float sum = 0.f;
+#pragma unroll
+                        for (int c = 0; c < NP * 8; ++c) {
+                            val[c] = (c < C) ? exp2f((val[c] - mx) * k2) : 0.f;
+                            sum += val[c];
+                        }
+                        const float inv_sum = __frcp_rn(sum);
+#pragma unroll
+                        for (int c = 0; c < NP * 8; ++c) val[c] *= inv_sum;
+                    }
+                    const int b = pix / hw, s = pix - b * hw;
+                    float* o = out + (size_t)b * C * hw + s;
+#pragma unroll
+                    for (int c = 0; c < NP * 8; ++c)
+                        if (c < C) o[(size_t)c * hw] = val[c];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
+    }
+}
+
+typedef CUresult (*css_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill);
+
+static css_tmap_encode_fn css_tmap_encoder() {
+    static css_tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (css_tmap_encode_fn)p;
+    }
+    return fn;
+}
+
+// channels-last rep pass: rows = the map itself ([N][256] fp32, 16-byte aligned).  sim_out / norms may each be NULL.
+int css_rep_pass_nhwc_tc(const float* rows, const float* prototypes, float* proto_scratch, int B, int C, int h, int w, int mode, float temp,
+                         float* sim_out, float* norms, const int32_t* guard, cudaStream_t st) {
+    const int hw = h * w, N = B * hw;
+    css_tmap_encode_fn enc = css_tmap_encoder();
+    if (!enc) {
+        css_set_error("css_rep_pass: cuTensorMapEncodeTiled is not available from this driver");
+        return CSS_E_ARG;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)CSS_D, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)CSS_D * 4};
+    const cuuint32_t box[2] = {TC_KC, TC_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(rows), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        css_set_error("css_rep_pass: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return CSS_E_ARG;
+    }
+    char* image = reinterpret_cast<char*>(proto_scratch);
+    if (prototypes) css_launch(proto_prep_tc_kernel, dim3(TC_N), dim3(CSS_D), (size_t)0, st, prototypes, image, C);
+    else cudaMemsetAsync(image, 0, 2 * TC_B_HALF, st);
+    const int n_tiles = (N + TC_M - 1) / TC_M;
+    const int sms = css_cached_sm_count();
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    const char* dbg_env = getenv("CSS_B200_NHWC_DBG");      // development knob: 1 = no MMAs, 2 = no correction MMAs (results are wrong)
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    cudaError_t e;
+    if (C <= 24) {
+        e = cudaFuncSetAttribute(rep_pass_nhwc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES);
+        if (e == cudaSuccess) e = css_launch(rep_pass_nhwc_kernel<3>, dim3(grid), dim3(TC_THREADS), (size_t)NL_SMEM_BYTES, st, tmap, (const char*)image, hw, N, C, mode, temp, sim_out, norms, guard, dbg);
+    } else {
+        e = cudaFuncSetAttribute(rep_pass_nhwc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES);
+        if (e == cudaSuccess) e = css_launch(rep_pass_nhwc_kernel<4>, dim3(grid), dim3(TC_THREADS), (size_t)NL_SMEM_BYTES, st, tmap, (const char*)image, hw, N, C, mode, temp, sim_out, norms, guard, dbg);
+    }
+    if (e != cudaSuccess) {
+        css_set_error("css_rep_pass (channels-last path): %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+
+extern "C" int css_rep_pass_nhwc(const void* rep_rows, int rep_dtype, const float* prototypes, float* proto_scratch, int B, int C, int D, int h,
+                                 int w, int mode, float temp, float* sim_out, float* norms, void* stream) {
+    CSS_CHECK_ARG(rep_rows && proto_scratch && (sim_out || norms), CSS_E_ARG, "css_rep_pass_nhwc: null pointer / nothing to do");
+    CSS_CHECK_ARG(!sim_out || prototypes, CSS_E_ARG, "css_rep_pass_nhwc: sim_out needs prototypes");
+    CSS_CHECK_ARG(B > 0 && h > 0 && w > 0, CSS_E_ARG, "css_rep_pass_nhwc: non-positive size");
+    CSS_CHECK_ARG(mode == CSS_SIM_COS || mode == CSS_SIM_SOFTMAX, CSS_E_ARG, "css_rep_pass_nhwc: bad mode %d", mode);
+    if (int e = css_check_dims(sim_out ? C : 1, D)) return e;
+    CSS_CHECK_ARG(rep_dtype == CSS_DTYPE_F32, CSS_E_DTYPE, "css_rep_pass_nhwc: only float32 channels-last maps are supported (dtype %d)", rep_dtype);
+    CSS_CHECK_ARG(((uintptr_t)rep_rows & 15) == 0, CSS_E_ARG, "css_rep_pass_nhwc: the map must be 16-byte aligned");
+    CSS_CHECK_ARG((long long)B * h * w < (1ll << 31) / CSS_CMAX, CSS_E_SIZE, "css_rep_pass_nhwc: too many pixels");
+    if (int e = css_rep_pass_nhwc_tc((const float*)rep_rows, prototypes, proto_scratch, B, sim_out ? C : 1, h, w, mode, temp, sim_out, norms, nullptr,
+                                     (cudaStream_t)stream))
+        return e;
+    CSS_CHECK_LAUNCH("css_rep_pass_nhwc", 2);
+    return 0;
+}
+
+// channels-last twin of css_rows_refresh: are the carried norms still those of THIS map?  `src_rows` is the map the norms were
+// computed from (kept alive by the caller), `rep_rows` the one the loss received (e.g. DDP's clone of it).
+__global__ void __launch_bounds__(256) rows_verify_rm_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int N,
+                                                             int32_t* __restrict__ meta) {
+    css_pdl_enter();
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= N) return;
+    const int d0 = (int)(((unsigned)p * 37u) & 63u);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bad |= a[(size_t)p * CSS_D + d0 + 64 * i] != b[(size_t)p * CSS_D + d0 + 64 * i];
+    if (bad) meta[CSS_META_ROWS_STALE] = 1;
+}
+
+extern "C" int css_rows_refresh_nhwc(const void* rep_rows, const void* src_rows, float* norms, float* proto_scratch, int32_t* meta, int B, int D,
+                                     int h, int w, void* stream) {
+    CSS_CHECK_ARG(rep_rows && src_rows && norms && proto_scratch && meta, CSS_E_ARG, "css_rows_refresh_nhwc: null pointer");
+    CSS_CHECK_ARG(B > 0 && h > 0 && w > 0 && D == CSS_D, CSS_E_ARG, "css_rows_refresh_nhwc: bad size");
+    CSS_CHECK_ARG(((uintptr_t)rep_rows & 15) == 0, CSS_E_ARG, "css_rows_refresh_nhwc: the map must be 16-byte aligned");
+    const int N = B * h * w;
+    cudaStream_t st = (cudaStream_t)stream;
+    css_launch(rows_verify_rm_kernel, dim3((N + 255) / 256), dim3(256), (size_t)0, st, (const uint32_t*)rep_rows, (const uint32_t*)src_rows, N, meta);
+    if (int e = css_rep_pass_nhwc_tc((const float*)rep_rows, nullptr, proto_scratch, B, 1, h, w, CSS_SIM_COS, 1.f, nullptr, norms,
+                                     meta + CSS_META_ROWS_STALE, st))
+        return e;
+    CSS_CHECK_LAUNCH("css_rows_refresh_nhwc", 2);
     return 0;
 }

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .ops import _cuda_f32, rep_rows
+from .ops import _cuda_f32, _proto_scratch, is_channels_last, rep_norms_nhwc, rep_rows, rows_view
 
 
 class _Workspace:
@@ -70,12 +70,24 @@ class _ContrastFn(torch.autograd.Function):
                              ptr(ws.hard_bits), ptr(ws.tile_counts), ptr(ws.valid_list), ptr(ws.hard_list), ptr(ws.meta), st),
               "css_select")
         how = cache.match(rep) if cache is not None else "miss"
-        if how == "miss":
+        nhwc = is_channels_last(rep)
+        if nhwc:                                # channels-last: the map is its own row table; only the norms are carried
+            rows = rows_view(rep)
+            if how == "miss":
+                norms = rep_norms_nhwc(rep)
+            else:
+                norms = cache.norms
+                if how == "verify":             # equal content at another address (DDP's output clone): checked on the device
+                    check(lib.css_rows_refresh_nhwc(ptr(rep), ptr(cache.src), ptr(norms), ptr(_proto_scratch(dev)), ptr(ws.meta), B2, D, h, w, st),
+                          "css_rows_refresh_nhwc")
+                    cache.rebind(rep)
+                    cache.rows = rows
+        elif how == "miss":
             rows, norms = rep_rows(rep)
         else:                                   # rows written by the same read that produced `prob`
             rows, norms = cache.rows, cache.norms
         rows_dt = _lib.DTYPE_BF16 if rows.dtype == torch.bfloat16 else _lib.DTYPE_F32
-        if how == "verify":                     # equal content at another address (DDP's output clone): checked on the device
+        if how == "verify" and not nhwc:        # equal content at another address (DDP's output clone): checked on the device
             check(lib.css_rows_refresh(ptr(rep), rows_dt, ptr(rows), ptr(norms), ptr(ws.meta), B2, D, h, w, st), "css_rows_refresh")
             cache.rebind(rep)
         check(lib.css_class_stats(ptr(rows), rows_dt, ptr(ws.valid_bits), ptr(ws.meta), N, C, D, ptr(ws.partials), ptr(ws.touched),
@@ -104,6 +116,7 @@ class _ContrastFn(torch.autograd.Function):
             e1.record()
             ev.append((e0, e1))
         ctx.shape = (B2, D, h, w)
+        ctx.nhwc_stride = tuple(rep.stride()) if nhwc else None
         ctx.rep_dtype = rep.dtype
         ctx.n_anchor = C * Q
         ctx.save_for_backward(anchor_px, grad_anchor)
@@ -119,6 +132,12 @@ class _ContrastFn(torch.autograd.Function):
         B2, D, h, w = ctx.shape
         lib = _lib.load()
         go = grad_out.detach().to(torch.float32).contiguous()
+        if ctx.nhwc_stride is not None:         # channels-last map: the gradient keeps the memory format (zero fill + row updates)
+            grad_rep = torch.empty_strided(ctx.shape, ctx.nhwc_stride, device=anchor_px.device, dtype=torch.float32)
+            with torch.cuda.device(anchor_px.device):
+                check(lib.css_grad_scatter_nhwc(ptr(go), ptr(anchor_px), ptr(grad_anchor), ctx.n_anchor, B2, D, h, w, ptr(grad_rep),
+                                                stream_ptr()), "css_grad_scatter_nhwc")
+            return grad_rep, None, None, None, None, None, None, None, None
         grad_rep = torch.empty(ctx.shape, device=anchor_px.device, dtype=torch.float32)
         with torch.cuda.device(anchor_px.device):
             check(lib.css_grad_scatter(ptr(go), ptr(anchor_px), ptr(grad_anchor), ctx.n_anchor, B2, D, h, w, ptr(grad_rep),
@@ -230,7 +249,7 @@ class Contrast_Loss(nn.Module):
         if mask.shape[1] != 1 or label.shape != prob.shape or label.shape[0] != rep.shape[0] or label.shape[2:] != rep.shape[2:]:
             raise RuntimeError("css_b200: label/prob must be [B2,C,h,w] and mask [B2,1,h,w] at rep resolution")
         want_grad = torch.is_grad_enabled() and rep.requires_grad
-        rep_c = rep if rep.is_contiguous() else rep.contiguous()
+        rep_c = rep if (rep.is_contiguous() or is_channels_last(rep)) else rep.contiguous()
         label_c, mask_c, prob_c = _cuda_f32(label, "label"), _cuda_f32(mask, "mask"), _cuda_f32(prob, "prob")
         if _indices is not None:
             a, n = _indices

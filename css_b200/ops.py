@@ -20,6 +20,19 @@ def _cuda_f32(t, name):
     return t.detach().contiguous()
 
 
+def is_channels_last(t):
+    """True for a float32 [B,256,h,w] map whose memory is [pixel][channel] (torch.channels_last) and 16-byte aligned: the layout
+    the channels-last kernels (css_rep_pass_nhwc, css_grad_scatter_nhwc) take without any copy."""
+    return (t.dim() == 4 and t.dtype == torch.float32 and t.shape[1] == _lib.D and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last) and t.data_ptr() % 16 == 0)
+
+
+def rows_view(rep):
+    """[N, 256] view of a channels-last map (no copy): row p = pixel id p."""
+    B, D, h, w = rep.shape
+    return rep.detach().permute(0, 2, 3, 1).reshape(B * h * w, D)
+
+
 def _cuda_rep(t, name="rep"):
     """Representation maps may be float32 or bfloat16 (BASELINE north_star); everything downstream is fp32."""
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -72,7 +85,7 @@ class RowsCache:
 
     def match(self, rep):
         src = self.src
-        if rep.shape != src.shape or rep.dtype != src.dtype or rep.device != src.device or not rep.is_contiguous():
+        if rep.shape != src.shape or rep.dtype != src.dtype or rep.device != src.device or rep.stride() != src.stride():
             return "miss"
         if rep.data_ptr() == src.data_ptr() and rep._version == self.version and src._version == self.version:
             return "same"
@@ -84,6 +97,19 @@ class RowsCache:
         """After css_rows_refresh the rows are those of `rep` (verified equal, or rewritten from it)."""
         self.src = rep.detach()
         self.version = rep._version
+
+
+def rep_norms_nhwc(rep):
+    """||x_p|| of a channels-last map (its rows are the map itself): one streaming read."""
+    B, D, h, w = rep.shape
+    norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32)
+    scratch = _proto_scratch(rep.device)
+    lib = _lib.load()
+    with torch.cuda.device(rep.device):
+        _timed_rep_pass("norms_nhwc",
+                        lambda: check(lib.css_rep_pass_nhwc(ptr(rep), _lib.DTYPE_F32, None, ptr(scratch), B, 1, D, h, w, _lib.SIM_COS, 1.0, None,
+                                                            ptr(norms), stream_ptr()), "css_rep_pass_nhwc"))
+    return norms
 
 
 def rep_rows(rep):
@@ -115,7 +141,30 @@ def _timed_rep_pass(label, launch):
     ev.append((e0, e1, label))
 
 
+def _sim_nhwc(rep, prototypes, mode, temp, with_rows):
+    """Channels-last map: similarities straight from the map (TMA + tcgen05, css_rep_pass_nhwc); the map is its own row table."""
+    rep = rep.detach()
+    prototypes = _cuda_f32(prototypes, "prototypes")
+    B, D, h, w = rep.shape
+    C = prototypes.shape[0]
+    if prototypes.shape[1] != D:
+        raise RuntimeError("css_b200: prototypes must be [C, D]")
+    out = torch.empty((B, C, h, w), device=rep.device, dtype=torch.float32)
+    norms = torch.empty(B * h * w, device=rep.device, dtype=torch.float32) if with_rows else None
+    scratch = _proto_scratch(rep.device)
+    lib = _lib.load()
+    with torch.cuda.device(rep.device):
+        _timed_rep_pass("student_nhwc" if with_rows else "teacher_nhwc",
+                        lambda: check(lib.css_rep_pass_nhwc(ptr(rep), _lib.DTYPE_F32, ptr(prototypes), ptr(scratch), B, C, D, h, w, mode, temp,
+                                                            ptr(out), ptr(norms), stream_ptr()), "css_rep_pass_nhwc"))
+    if with_rows:
+        out._css_rows = RowsCache(rep, rows_view(rep), norms)
+    return out
+
+
 def _sim(rep, prototypes, mode, temp, with_rows=False):
+    if isinstance(rep, torch.Tensor) and rep.is_cuda and is_channels_last(rep):
+        return _sim_nhwc(rep, prototypes, mode, temp, with_rows)
     rep, dt = _cuda_rep(rep)
     prototypes = _cuda_f32(prototypes, "prototypes")
     B, D, h, w = rep.shape

@@ -96,6 +96,22 @@ int css_sim_map(const void* rep, int rep_dtype, const float* prototypes, float* 
  * environment variable.  Both meet the path's tolerances (similarities abs 2e-6, labels identical away from 1e-5 near-ties). */
 int css_set_rep_pass_path(int use_tc);
 
+/* ---- channels-last maps (extension; the reference's maps are NCHW) ---------------------------------------------------------------
+ * A representation map produced by a channels_last network (torch.channels_last: strides (h*w*D, 1, w*D, D)) is, in memory,
+ * [pixel][D]: it IS the pixel-major row table the loss gathers from.  css_rep_pass_nhwc computes the similarities (a) straight
+ * from it -- 2-D TMA tiles into shared memory, tcgen05.mma kind::tf32 with an exact hi/lo split, TMEM accumulators -- and
+ * ||x_p||; there is no pixel-major copy to write.  sim_out [B,C,h,w] f32 (NCHW, as the callers expect) and norms f32[N] may
+ * each be NULL (norms alone: prototypes may be NULL).  float32 only; rep_rows must be 16-byte aligned.
+ * css_grad_scatter_nhwc writes the dense gradient in the same memory format: zero fill + one row update per anchor.
+ * css_rows_refresh_nhwc is the twin of css_rows_refresh: `src_rows` is the map the carried norms came from.
+ */
+int css_rep_pass_nhwc(const void* rep_rows, int rep_dtype, const float* prototypes, float* proto_scratch,
+                      int B, int C, int D, int h, int w, int mode, float temp, float* sim_out, float* norms, void* stream);
+int css_grad_scatter_nhwc(const float* grad_out, const int32_t* anchor_px, const float* grad_anchor,
+                          int n_anchor, int B2, int D, int h, int w, float* grad_rows, void* stream);
+int css_rows_refresh_nhwc(const void* rep_rows, const void* src_rows, float* norms, float* proto_scratch, int32_t* meta,
+                          int B, int D, int h, int w, void* stream);
+
 /* ---- carried rows: "are these still the rows of THIS map?" ---------------------------------------------------------------
  * The reference wraps the model in DistributedDataParallel(find_unused_parameters=True) (mix_label.py:76-77,
  * cross_label.py, ori_pseudo.py alike); DDP's output sink clones rep_all, so the loss (loss.py:75) receives equal content at

@@ -142,6 +142,32 @@ int main() {
         for (int k = 0; k < KTOT; ++k) memcpy(b_img + b_offset(n, k), &B[n][k], 4);
     cudaMemcpy(db, b_img, 65536, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    {   // does the tensor core TRUNCATE or ROUND an fp32 bit pattern to TF32?  A[0][0] = 1 + 2^-11 + 2^-12, B[0][0] = 1, rest 0
+        static float A2[M][KTOT], B2[N][KTOT];
+        memset(A2, 0, sizeof(A2));
+        memset(B2, 0, sizeof(B2));
+        A2[0][0] = 1.0f + 1.0f / 2048 + 1.0f / 4096;
+        B2[0][0] = 1.0f;
+        A2[1][0] = 1.0f;
+        B2[1][0] = 1.0f + 1.0f / 2048 + 1.0f / 4096;
+        memset(a_img, 0, 65536);
+        memset(b_img, 0, 65536);
+        for (int m = 0; m < M; ++m)
+            for (int k = 0; k < KTOT; ++k) memcpy(a_img + a_offset(0, m, k), &A2[m][k], 4);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < KTOT; ++k) memcpy(b_img + b_offset(n, k), &B2[n][k], 4);
+        cudaMemcpy(da, a_img, 65536, cudaMemcpyHostToDevice);
+        cudaMemcpy(db, b_img, 65536, cudaMemcpyHostToDevice);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+        umma_test<<<1, 128, 140 * 1024>>>(da, db, 65536, 65536, idesc, 16, 1024, 2, 0, 0, dout, ddbg);
+        cudaDeviceSynchronize();
+        cudaMemcpy(hout, dout, sizeof(hout), cudaMemcpyDeviceToHost);
+        printf("TF32 operand conversion: A=1+2^-11+2^-12 times 1 -> %.10f (1.0 = truncated, 1.0009765625 = rounded); 1 times B=1+2^-11+2^-12 -> %.10f\n",
+               hout[0 * N + 0], hout[1 * N + 1]);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < KTOT; ++k) memcpy(b_img + b_offset(n, k), &B[n][k], 4);
+        cudaMemcpy(db, b_img, 65536, cudaMemcpyHostToDevice);
+    }
     for (auto& v : vs) {
         memset(a_img, 0, 65536);
         for (int m = 0; m < M; ++m)

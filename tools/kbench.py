@@ -49,8 +49,10 @@ def main():
     dev = torch.device("cuda")
     P = a.pool
     rdt = torch.bfloat16 if a.bf16 else torch.float32
-    rep_u = [host["rep_u"].to(dev).to(rdt) + 0 for _ in range(P)]
-    rep_all = [host["rep_all"].to(dev).to(rdt) + 0 for _ in range(P)]
+    nhwc = cfg.get("layout") == "nhwc"
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    rep_u = [(host["rep_u"].to(dev).to(rdt) + 0).contiguous(memory_format=fmt) for _ in range(P)]
+    rep_all = [(host["rep_all"].to(dev).to(rdt) + 0).contiguous(memory_format=fmt) for _ in range(P)]
     pred_u = host["pred_u"].to(dev)
     label, mask = host["label"].to(dev), host["mask"].to(dev)
     protos = host["prototypes"].to(dev)
@@ -100,7 +102,8 @@ def main():
     one = torch.ones((), device=dev)
 
     def scatter(i):
-        check(lib.css_grad_scatter(ptr(one), ptr(anchor_px), ptr(grad_anchor), C * Q, B2, D, h, w, ptr(grads[i % P]), stream_ptr()), "scatter")
+        fn = lib.css_grad_scatter_nhwc if nhwc else lib.css_grad_scatter
+        check(fn(ptr(one), ptr(anchor_px), ptr(grad_anchor), C * Q, B2, D, h, w, ptr(grads[i % P]), stream_ptr()), "scatter")
 
     g0 = torch.Generator().manual_seed(0)
     ll = torch.randint(-1, C, (B, H, W), generator=g0).to(dev)
@@ -141,7 +144,7 @@ def main():
     res["cut_mix image + 3 maps (8(f)-2, not in path sum)"] = timeit(cutmix, a.iters)
     res["select (3 kernels)"] = timeit(select, a.iters)
     res["class_stats (+reduce)"] = timeit(stream, a.iters)
-    res["rep_rows only (ori flow)"] = timeit(lambda i: css_b200.ops.rep_rows(rep_all[i % P]), a.iters)
+    res["rep_rows only (ori flow)"] = timeit(lambda i: (css_b200.ops.rep_norms_nhwc if nhwc else css_b200.ops.rep_rows)(rep_all[i % P]), a.iters)
     res["proto_ema (+cdf)"] = timeit(ema, a.iters)
     res["score_ce fwd+grad (+reduce)"] = timeit(score, a.iters)
     res["score_ce fwd only"] = timeit(lambda i: score(i, False), a.iters)
