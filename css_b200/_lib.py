@@ -36,6 +36,7 @@ SIGNATURES = {
     "css_select": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "css_rep_pass": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P]),
     "css_set_rep_pass_path": (c_int, [c_int]),
+    "css_set_scorer_path": (c_int, [c_int]),
     "css_rep_pass_nhwc": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "css_grad_scatter_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "css_rows_refresh_nhwc": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),

@@ -14,6 +14,8 @@
 // candidates are produced one per lane (Philox draw or fed index -> rotated segment -> class list lookup) and handed to
 // the groups by shuffle.  The four warp states are merged through shared memory in a fixed order (deterministic).
 #include "css_common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 #define SC_WARPS 4
 #define SC_THREADS (SC_WARPS * 32)
@@ -68,19 +70,21 @@ struct SlotTables {
 
 __device__ __forceinline__ void build_slot_tables(SlotTables& t, const int32_t* __restrict__ meta,
                                                   const float* __restrict__ class_cdf, int k, int V) {
+    // warp 0: one segment per lane, the prefix offsets by a shuffle scan (two dependent loads in all, not one per class)
     if (threadIdx.x < CSS_CMAX) {
         const int i = threadIdx.x;
         t.cdf[i] = class_cdf[k * CSS_CMAX + i];
-        t.rot_cls[i] = (i < V - 1) ? meta[CSS_META_CLS_OF_SLOT + (k + 1 + i) % V] : -1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < V - 1; ++i) {
-            t.rot_off[i] = run;
-            run += meta[CSS_META_N_VALID + t.rot_cls[i]];
+        const int cls = (i < V - 1) ? meta[CSS_META_CLS_OF_SLOT + (k + 1 + i) % V] : -1;
+        t.rot_cls[i] = cls;
+        const int nv = (cls >= 0) ? meta[CSS_META_N_VALID + cls] : 0;
+        int incl = nv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (i >= o) incl += up;
         }
-        for (int i = V - 1; i <= CSS_CMAX; ++i) t.rot_off[i] = run;
+        t.rot_off[i] = incl - nv;                      // segments past V-2 are empty: their offset is the total
+        if (i == CSS_CMAX - 1) t.rot_off[CSS_CMAX] = incl;
     }
     __syncthreads();
 }
@@ -483,6 +487,151 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     finish_query<WANT_GRAD, RT>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// The same scorer with the candidate rows staged through shared memory by 16-byte asynchronous copies (cp.async.cg, LDGSTS):
+// the register kernel above can keep only ONE row per 8-lane group in flight (row + gradient state + anchor fill its 96
+// registers), so a warp waits out a full L2 round trip for every four rows and the SM holds 20 warps x 4 KB = 80 KB in flight.
+// Here every warp owns a ring of RING_STAGES x 4 rows in shared memory; the copies for step s + RING_STAGES - 1 are issued
+// before step s is scored, so (RING_STAGES - 1) x 4 KB per warp stay in flight WHILE the warp computes, at no register cost.
+// A lane copies exactly the 16-byte chunks it later reads (chunk i*8 + l8 of its group's row), so cp.async.wait_group alone
+// orders a lane's reads after its own copies and no warp barrier is needed; a quarter-warp reads 128 contiguous bytes
+// (conflict-free).  The anchor lives in registers (re-reading it from shared memory per row would put 3 KB of shared-memory
+// traffic on every gathered KB).  fp32 rows with the gradient; everything else stays on the register kernel.
+// -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+
+#define RING_STAGE_BYTES (4 * CSS_D * 4)          // four fp32 rows, one per 8-lane group
+
+// ids of the warp's candidates 32 b + lane: negative j - 1 = warp + SC_WARPS n  ->  pixel-major row, or -2 past the end
+template <bool FED>
+__device__ __forceinline__ int ring_candidate_row(const SlotTables& tb, const DrawKey& dk, const int32_t* __restrict__ neg_idx,
+                                                  const int32_t* __restrict__ valid_list, int k, int q, int Q, int Nn, int N, int n, int cnt) {
+    if (n >= cnt) return -2;
+    const int jm1 = (threadIdx.x >> 5) + SC_WARPS * n;
+    int seg, within;
+    if (FED) {
+        const int idx = neg_idx[((size_t)k * Q + q) * Nn + jm1];
+        seg = upper_bound32(tb.rot_off + 1, idx);
+        within = idx - tb.rot_off[seg];
+    } else {
+        within = draw_negative(dk, k, q, jm1, tb.cdf, tb.rot_off, seg);
+    }
+    return valid_list[(size_t)tb.rot_cls[seg] * N + within];
+}
+
+template <bool FIX, bool FED, int STAGES, int MINB>
+__global__ void __launch_bounds__(SC_THREADS, MINB) score_ce_ring_kernel(
+    const float* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
+    const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
+    const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
+    int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px, float4* __restrict__ grad_anchor) {
+    css_pdl_enter();
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ SlotTables tb;
+    __shared__ QueryShared sh;
+    const int k = blockIdx.y, q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int V = meta[CSS_META_V];
+    const int c = (k < V) ? meta[CSS_META_CLS_OF_SLOT + k] : 0;
+    const int n_hard = (k < V) ? meta[CSS_META_N_HARD + c] : 0;
+    if (k >= V || V <= 1 || n_hard == 0) {
+        if (threadIdx.x == 0) {
+            loss_kq[k * Q + q] = 0.f;
+            anchor_px[k * Q + q] = -1;
+        }
+        return;
+    }
+    const int grp = lane >> 3, l8 = lane & 7;
+    const DrawKey dk = make_key(seed, ((uint64_t)(uint32_t)meta[CSS_META_DRAW_OFFSET + 1] << 32) | (uint32_t)meta[CSS_META_DRAW_OFFSET]);
+    const int ai = FED ? anchor_idx[k * Q + q] : draw_anchor(dk, k, q, n_hard);
+    const int pa = hard_list[(size_t)c * N + ai];              // in flight while the slot tables are built
+    build_slot_tables(tb, meta, class_cdf, k, V);
+
+    // warp w owns the negatives j - 1 = w + SC_WARPS n, n < cnt, four per step (one per group)
+    const int cnt = (Nn - warp + SC_WARPS - 1) / SC_WARPS;
+    const int T = (cnt + 3) >> 2;
+    int cur_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, lane, cnt);
+    int nxt_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, 32 + lane, cnt);
+
+    // this lane's 16-byte chunks of the ring: stage s, chunk i at lane_base + s * RING_STAGE_BYTES + i * 128
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_smem) + warp * (STAGES * RING_STAGE_BYTES) + grp * (CSS_D * 4) + l8 * 16;
+    const char* rows_b = reinterpret_cast<const char*>(rows) + l8 * 16;
+    auto issue = [&](uint32_t stage_off, int row) {
+        const char* src = rows_b + (size_t)max(row, 0) * (CSS_D * 4);      // past the end: any finite row, weight 0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(ring0 + stage_off + i * 128, src + i * 128);
+    };
+    uint32_t wr_off = 0, rd_off = 0;
+#pragma unroll
+    for (int p = 0; p < STAGES - 1; ++p) {
+        issue(wr_off, __shfl_sync(0xffffffffu, cur_row, p * 4 + grp));
+        cp_async_commit();
+        wr_off += RING_STAGE_BYTES;
+    }
+
+    float4 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = row_f4(rows, (size_t)pa, i * 8 + l8);
+    const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);       // cosine_similarity eps (loss.py:146)
+    const float scale2 = 1.4426950408889634f / temp;
+    float cur_inv = 1.f / fmaxf(norms[max(cur_row, 0)], 1e-8f);
+
+    Online st;
+    st.m = FIX ? scale2 : -INFINITY;
+    st.l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // candidate 0 = the (updated) prototype of class c (loss.py:143-144): scored by every warp, kept by warp 0 / group 0
+    float z0, cos_pos;
+    {
+        const float4* pp = proto_hat + (size_t)c * (CSS_D / 4) + l8;
+        float4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __ldg(pp + i * 8);
+        cos_pos = group_sum8(dot8(a, r)) * inv_na;
+        z0 = cos_pos * scale2;
+        online_update<true, FIX>(st, z0, warp == 0 && grp == 0, 1.f, r);
+    }
+
+    // Batches of 8 steps (the ids of 32 candidates live one per lane).  A partial last batch runs all 8 steps: candidates past the
+    // end carry weight 0 and copy row 0 (the loop has a single exit, which keeps the accumulators out of local memory).
+#pragma unroll 1
+    for (int b = 0; b * 8 < T; ++b) {
+        float nxt_nrm = 1.f;
+#pragma unroll 1
+        for (int t = 0; t < 8; ++t) {
+            {   // copies of step s + STAGES - 1
+                const int tp = t + (STAGES - 1);
+                const int prow = __shfl_sync(0xffffffffu, (tp < 8) ? cur_row : nxt_row, (tp & 7) * 4 + grp);
+                issue(wr_off, prow);
+                cp_async_commit();
+                wr_off = (wr_off + RING_STAGE_BYTES == STAGES * RING_STAGE_BYTES) ? 0u : wr_off + RING_STAGE_BYTES;
+            }
+            cp_async_wait<STAGES - 1>();
+            const int row = __shfl_sync(0xffffffffu, cur_row, t * 4 + grp);
+            const float inv = __shfl_sync(0xffffffffu, cur_inv, t * 4 + grp);
+            float4 r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = lds128(ring0 + rd_off + i * 128);
+            rd_off = (rd_off + RING_STAGE_BYTES == STAGES * RING_STAGE_BYTES) ? 0u : rd_off + RING_STAGE_BYTES;
+            const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+            online_update<true, FIX>(st, cosv * scale2, row >= 0, inv, r);
+            if (t == 3) nxt_nrm = norms[max(nxt_row, 0)];       // the id has landed by now; used after the batch
+        }
+        cur_row = nxt_row;
+        cur_inv = 1.f / fmaxf(nxt_nrm, 1e-8f);
+        nxt_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, (b + 2) * 32 + lane, cnt);
+    }
+    cp_async_wait<0>();
+    finish_query<true, float>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
+}
+
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_kq, const int32_t* __restrict__ meta, int Q,
                                                           float* __restrict__ loss) {
@@ -507,6 +656,38 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
         for (int i = 0; i < 8; ++i) t += part[i];
         *loss = (V > 1) ? t / ((float)Q * (float)V) : 0.f;
     }
+}
+
+// which kernel scores fp32 rows with the gradient: 0 = register kernel, 1..3 = shared-memory ring (stages x CTAs/SM = 3x4, 4x3, 2x4);
+// css_set_scorer_path() overrides CSS_B200_SCORER=reg|ring|ring4|ring2, which overrides the default
+#ifndef CSS_SCORER_DEFAULT
+#define CSS_SCORER_DEFAULT 1
+#endif
+static int g_scorer_path = -1;
+extern "C" int css_set_scorer_path(int path) {
+    g_scorer_path = (path < 0 || path > 3) ? -1 : path;
+    return 0;
+}
+static int css_scorer_path() {
+    if (g_scorer_path >= 0) return g_scorer_path;
+    static int env = -1;
+    if (env < 0) {
+        const char* v = getenv("CSS_B200_SCORER");
+        env = !v ? CSS_SCORER_DEFAULT : !strcmp(v, "reg") ? 0 : !strcmp(v, "ring") ? 1 : !strcmp(v, "ring4") ? 2 : !strcmp(v, "ring2") ? 3 : CSS_SCORER_DEFAULT;
+    }
+    return env;
+}
+
+template <bool FIX, bool FED, int STAGES, int MINB, typename... Args>
+static cudaError_t launch_ring(dim3 grid, cudaStream_t st, Args... args) {
+    static bool configured = false;
+    const size_t smem = (size_t)SC_WARPS * STAGES * RING_STAGE_BYTES;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(score_ce_ring_kernel<FIX, FED, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    return css_launch(score_ce_ring_kernel<FIX, FED, STAGES, MINB>, grid, dim3(SC_THREADS), smem, st, args...);
 }
 
 extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms, const float* proto_hat, const float* class_cdf,
@@ -538,7 +719,17 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
             else score_ce_kernel<false, sizeof(RT_) == 4, false, false, RT_><<<grid, SC_THREADS, 0, st>>>(SC_ARGS(RT_));         \
         }                                                                                                           \
     } while (0)
-    if (rows_dtype == CSS_DTYPE_F32) SC_RUN(float);
+    const int path = (grad_anchor && rows_dtype == CSS_DTYPE_F32) ? css_scorer_path() : 0;
+    if (path > 0) {
+#define RING_ARGS (const float*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, (const int32_t*)meta, anchor_idx, neg_idx, \
+                  seed, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
+#define RING_RUN(S_, B_) (neg_idx ? (fix ? launch_ring<true, true, S_, B_>(grid, st, RING_ARGS) : launch_ring<false, true, S_, B_>(grid, st, RING_ARGS)) \
+                                  : (fix ? launch_ring<true, false, S_, B_>(grid, st, RING_ARGS) : launch_ring<false, false, S_, B_>(grid, st, RING_ARGS)))
+        const cudaError_t e = path == 1 ? RING_RUN(3, 4) : path == 2 ? RING_RUN(4, 3) : RING_RUN(2, 4);
+#undef RING_RUN
+#undef RING_ARGS
+        if (e != cudaSuccess) { css_set_error("css_score_ce: ring launch: %s", cudaGetErrorString(e)); return (int)e; }
+    } else if (rows_dtype == CSS_DTYPE_F32) SC_RUN(float);
     else SC_RUN(__nv_bfloat16);
 #undef SC_RUN
 #undef SC_ARGS

@@ -439,3 +439,39 @@ def test_tiny_and_ragged_shapes(B2, C, h, w, Q, Nn):
     # from a few dozen pixels: elements far below the row's scale carry fp32 summation-order noise of ~1e-5 of that scale
     np.testing.assert_allclose(grad.cpu().numpy(), g_or, rtol=RTOL, atol=2e-5 * max(np.abs(g_or).max(), 1e-30))
     np.testing.assert_allclose(protos.cpu().numpy(), p_or, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("Nn", [1, 5, 50, 100, 512, 700])
+@pytest.mark.parametrize("temp", [0.5, 0.02])
+def test_scorer_paths_agree(Nn, temp):
+    """css_set_scorer_path: the shared-memory ring kernels (3 stages x 4 CTAs/SM, 4 x 3, 2 x 4) draw the same candidates as the
+    register kernel and agree with it to rounding (another summation order), on full and ragged candidate batches, with the
+    draws made on the fly and fed, with the fixed-reference and the online-max softmax (temp 0.02)."""
+    import css_b200
+    from css_b200 import _lib, synth
+    lib = _lib.load()
+    B2, C, h, w, Q = 2, 7, 19, 23, 12
+    d = synth.student_batch(B2, C, h, w, seed=11 + Nn, block=3)
+    kw = dict(num_queries=Q, num_negatives=Nn, temp=temp, strong_threshold=0.97, alpha=0.99)
+    rep, label, mask, prob = (d[k].numpy() for k in ("rep", "label", "mask", "prob"))
+    protos0 = synth.warm_prototypes(C, seed=8)
+    out = {}
+    try:
+        for path in (0, 1, 2, 3):
+            lib.css_set_scorer_path(path)
+            crit = css_b200.Contrast_Loss(seed=9, **kw).cuda()
+            loss, grad = run_gpu(crit, rep, label, mask, prob, protos0.clone().cuda())
+            a, n = crit.sample_indices(9, 0)
+            loss_fed, grad_fed = run_gpu(crit, rep, label, mask, prob, protos0.clone().cuda(), (a, n))
+            assert loss_fed.item() == loss.item()
+            torch.testing.assert_close(grad_fed, grad, rtol=1e-6, atol=1e-9)
+            out[path] = (loss.item(), grad.cpu().numpy(), crit.last["anchor_px"].cpu().numpy())
+    finally:
+        lib.css_set_scorer_path(-1)
+    l0, g0, px0 = out[0]
+    assert np.abs(g0).max() > 0
+    for path in (1, 2, 3):
+        l, g, px = out[path]
+        assert np.array_equal(px, px0)
+        np.testing.assert_allclose(l, l0, rtol=2e-6)
+        np.testing.assert_allclose(g, g0, rtol=1e-5, atol=2e-6 * np.abs(g0).max())
