@@ -374,8 +374,7 @@ __global__ void __launch_bounds__(SC_THREADS, (WANT_GRAD && !ASMEM) ? 4 : 5) sco
     const RT* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
     const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
     const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
-    uint64_t offset, int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px,
-    float4* __restrict__ grad_anchor) {
+    int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px, float4* __restrict__ grad_anchor) {
     css_pdl_enter();
     __shared__ SlotTables tb;
     __shared__ QueryShared sh;
@@ -632,6 +631,156 @@ __global__ void __launch_bounds__(SC_THREADS, MINB) score_ce_ring_kernel(
     finish_query<true, float>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Hybrid with the bulk-copy engine: LDGSTS copies queue on the SM's L1 data pipe like the register loads do (global wavefronts +
+// the shared-memory write), which is why the ring above loses.  Here every PERIOD-th step of a warp comes in through cp.async.bulk
+// (the TMA unit writes shared memory on its own port, completion on an mbarrier) and the other steps are plain register loads, so
+// the two paths fetch concurrently: 4 KB per warp in flight on each.  The bulk path alone tops out near 31 B/clk/SM (round 1).
+// NBUF buffers of four rows per warp; buffered step j uses buffer j % NBUF, refilled NBUF buffered steps (NBUF * PERIOD steps) ahead.
+// -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sc_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SC_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SC_DONE;\n\t"
+        "bra SC_WAIT_LOOP;\n\t"
+        "SC_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sc_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar) : "memory");
+}
+
+template <bool FIX, bool FED, int PERIOD, int NBUF, int MINB>
+__global__ void __launch_bounds__(SC_THREADS, MINB) score_ce_bulk_kernel(
+    const float* __restrict__ rows, const float* __restrict__ norms, const float4* __restrict__ proto_hat,
+    const float* __restrict__ class_cdf, const int32_t* __restrict__ valid_list, const int32_t* __restrict__ hard_list,
+    const int32_t* __restrict__ meta, const int32_t* __restrict__ anchor_idx, const int32_t* __restrict__ neg_idx, uint64_t seed,
+    int N, int Q, int Nn, float temp, float* __restrict__ loss_kq, int32_t* __restrict__ anchor_px, float4* __restrict__ grad_anchor) {
+    static_assert(NBUF * PERIOD <= 8 && 8 % PERIOD == 0 && (8 / PERIOD) % NBUF == 0, "refill distance must stay inside the next id batch");
+    css_pdl_enter();
+    __shared__ __align__(128) unsigned char stage_smem[SC_WARPS * NBUF * RING_STAGE_BYTES];
+    __shared__ __align__(8) unsigned long long bars[SC_WARPS * NBUF];
+    __shared__ SlotTables tb;
+    __shared__ QueryShared sh;
+    const int k = blockIdx.y, q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int V = meta[CSS_META_V];
+    const int c = (k < V) ? meta[CSS_META_CLS_OF_SLOT + k] : 0;
+    const int n_hard = (k < V) ? meta[CSS_META_N_HARD + c] : 0;
+    if (k >= V || V <= 1 || n_hard == 0) {
+        if (threadIdx.x == 0) {
+            loss_kq[k * Q + q] = 0.f;
+            anchor_px[k * Q + q] = -1;
+        }
+        return;
+    }
+    const int grp = lane >> 3, l8 = lane & 7;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars) + warp * NBUF * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) sc_mbar_init(bar0 + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const DrawKey dk = make_key(seed, ((uint64_t)(uint32_t)meta[CSS_META_DRAW_OFFSET + 1] << 32) | (uint32_t)meta[CSS_META_DRAW_OFFSET]);
+    const int ai = FED ? anchor_idx[k * Q + q] : draw_anchor(dk, k, q, n_hard);
+    const int pa = hard_list[(size_t)c * N + ai];
+    build_slot_tables(tb, meta, class_cdf, k, V);              // (its barrier also publishes the mbarrier inits)
+
+    const int cnt = (Nn - warp + SC_WARPS - 1) / SC_WARPS;
+    const int T = (cnt + 3) >> 2;
+    int cur_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, lane, cnt);
+    int nxt_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, 32 + lane, cnt);
+
+    const uint32_t grp_buf = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * (NBUF * RING_STAGE_BYTES) + grp * (CSS_D * 4);
+    const uint32_t buf = grp_buf + l8 * 16;
+    auto refill = [&](int ib, int row) {       // the group's leader copies the group's row; lane 0 arms the warp's barrier
+        if (lane == 0) sc_mbar_expect_tx(bar0 + ib * 8, RING_STAGE_BYTES);
+        if (l8 == 0) sc_bulk_g2s(grp_buf + ib * RING_STAGE_BYTES, reinterpret_cast<const char*>(rows) + (size_t)max(row, 0) * (CSS_D * 4), CSS_D * 4, bar0 + ib * 8);
+    };
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) refill(i, __shfl_sync(0xffffffffu, cur_row, i * PERIOD * 4 + grp));
+
+    float4 a[8];                                               // the anchor stays in registers (128 registers, 4 CTAs/SM)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = row_f4(rows, (size_t)pa, i * 8 + l8);
+    const float inv_na = 1.f / fmaxf(norms[pa], 1e-8f);
+    const float scale2 = 1.4426950408889634f / temp;
+    float cur_inv = 1.f / fmaxf(norms[max(cur_row, 0)], 1e-8f);
+
+    Online st;
+    st.m = FIX ? scale2 : -INFINITY;
+    st.l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float z0, cos_pos;
+    {
+        const float4* pp = proto_hat + (size_t)c * (CSS_D / 4) + l8;
+        float4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __ldg(pp + i * 8);
+        cos_pos = group_sum8(dot8(a, r)) * inv_na;
+        z0 = cos_pos * scale2;
+        online_update<true, FIX>(st, z0, warp == 0 && grp == 0, 1.f, r);
+    }
+
+    uint32_t parity = 0;
+#pragma unroll 1
+    for (int b = 0; b * 8 < T; ++b) {
+        float nxt_nrm = 1.f;
+        const bool more = (b + 1) * 8 < T;               // a next batch exists: refills may reach into it
+#pragma unroll 1
+        for (int tb0 = 0; tb0 < 8; tb0 += NBUF * PERIOD) {
+#pragma unroll
+          for (int ib = 0; ib < NBUF; ++ib) {
+            const int t0 = tb0 + ib * PERIOD;
+            {   // buffered step
+                const int row = __shfl_sync(0xffffffffu, cur_row, t0 * 4 + grp);
+                const float inv = __shfl_sync(0xffffffffu, cur_inv, t0 * 4 + grp);
+                sc_mbar_wait(bar0 + ib * 8, parity);
+                float4 r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = lds128(buf + ib * RING_STAGE_BYTES + i * 128);
+                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                __syncwarp();                                   // every lane has read the buffer
+                const int tp = t0 + NBUF * PERIOD;
+                const int prow = __shfl_sync(0xffffffffu, (tp < 8) ? cur_row : nxt_row, (tp & 7) * 4 + grp);
+                if (tp < 8 || more) refill(ib, prow);
+                online_update<true, FIX>(st, cosv * scale2, row >= 0, inv, r);
+            }
+#pragma unroll
+            for (int u = 1; u < PERIOD; ++u) {                  // register steps
+                const int t = t0 + u;
+                const int row = __shfl_sync(0xffffffffu, cur_row, t * 4 + grp);
+                const float inv = __shfl_sync(0xffffffffu, cur_inv, t * 4 + grp);
+                const float4* p = reinterpret_cast<const float4*>(rows) + (size_t)max(row, 0) * (CSS_D / 4) + l8;
+                float4 r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = __ldg(p + i * 8);
+                const float cosv = group_sum8(dot8(a, r)) * (inv_na * inv);
+                online_update<true, FIX>(st, cosv * scale2, row >= 0, inv, r);
+            }
+            if (t0 == 4) nxt_nrm = norms[max(nxt_row, 0)];
+          }
+          parity ^= 1u;
+        }
+        cur_row = nxt_row;
+        cur_inv = 1.f / fmaxf(nxt_nrm, 1e-8f);
+        nxt_row = ring_candidate_row<FED>(tb, dk, neg_idx, valid_list, k, q, Q, Nn, N, (b + 2) * 32 + lane, cnt);
+    }
+    finish_query<true, float>(st, z0, cos_pos, sh, rows, proto_hat, inv_na, pa, c, k, q, Q, V, temp, loss_kq, anchor_px, grad_anchor);
+}
+
 // loss = (1/V) sum_k (1/Q) sum_q loss_kq ; exactly 0 when V <= 1 (loss.py:116-117,149).  One block, fixed-order tree.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_kq, const int32_t* __restrict__ meta, int Q,
                                                           float* __restrict__ loss) {
@@ -658,14 +807,14 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
     }
 }
 
-// which kernel scores fp32 rows with the gradient: 0 = register kernel, 1..3 = shared-memory ring (stages x CTAs/SM = 3x4, 4x3, 2x4);
-// css_set_scorer_path() overrides CSS_B200_SCORER=reg|ring|ring4|ring2, which overrides the default
+// which kernel scores fp32 rows with the gradient: 0 = register kernel (default), 1 = shared-memory ring (2 stages, cp.async),
+// 2 = register / bulk-copy hybrid; css_set_scorer_path() overrides CSS_B200_SCORER=reg|ring|bulk, which overrides the default
 #ifndef CSS_SCORER_DEFAULT
-#define CSS_SCORER_DEFAULT 1
+#define CSS_SCORER_DEFAULT 0
 #endif
 static int g_scorer_path = -1;
 extern "C" int css_set_scorer_path(int path) {
-    g_scorer_path = (path < 0 || path > 3) ? -1 : path;
+    g_scorer_path = (path < 0 || path > 2) ? -1 : path;
     return 0;
 }
 static int css_scorer_path() {
@@ -673,7 +822,7 @@ static int css_scorer_path() {
     static int env = -1;
     if (env < 0) {
         const char* v = getenv("CSS_B200_SCORER");
-        env = !v ? CSS_SCORER_DEFAULT : !strcmp(v, "reg") ? 0 : !strcmp(v, "ring") ? 1 : !strcmp(v, "ring4") ? 2 : !strcmp(v, "ring2") ? 3 : CSS_SCORER_DEFAULT;
+        env = !v ? CSS_SCORER_DEFAULT : !strcmp(v, "reg") ? 0 : !strcmp(v, "ring") ? 1 : !strcmp(v, "bulk") ? 2 : CSS_SCORER_DEFAULT;
     }
     return env;
 }
@@ -688,6 +837,11 @@ static cudaError_t launch_ring(dim3 grid, cudaStream_t st, Args... args) {
         configured = true;
     }
     return css_launch(score_ce_ring_kernel<FIX, FED, STAGES, MINB>, grid, dim3(SC_THREADS), smem, st, args...);
+}
+
+template <bool FIX, bool FED, int PERIOD, int NBUF, int MINB, typename... Args>
+static cudaError_t launch_bulk(dim3 grid, cudaStream_t st, Args... args) {
+    return css_launch(score_ce_bulk_kernel<FIX, FED, PERIOD, NBUF, MINB>, grid, dim3(SC_THREADS), (size_t)0, st, args...);
 }
 
 extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms, const float* proto_hat, const float* class_cdf,
@@ -707,8 +861,8 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
     dim3 grid(Q, C);
     // fixed-reference softmax whenever 2^(-2 log2(e)/temp) is far from fp32 underflow (temp > ~0.024); online max otherwise
     const bool fix = (2.f * 1.4426950408889634f / temp) < 120.f;
-#define SC_ARGS(RT_) (const RT_*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, meta, anchor_idx, neg_idx, seed, \
-                     offset, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
+#define SC_ARGS(RT_) (const RT_*)rows, norms, (const float4*)proto_hat, class_cdf, valid_list, hard_list, (const int32_t*)meta, anchor_idx, neg_idx, seed, \
+                     N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
 #define SC_RUN(RT_)                                                                                                 \
     do {                                                                                                            \
         if (grad_anchor) {                                                                                          \
@@ -725,7 +879,10 @@ extern "C" int css_score_ce(const void* rows, int rows_dtype, const float* norms
                   seed, N, Q, Nn, temp, loss_kq, anchor_px, (float4*)grad_anchor
 #define RING_RUN(S_, B_) (neg_idx ? (fix ? launch_ring<true, true, S_, B_>(grid, st, RING_ARGS) : launch_ring<false, true, S_, B_>(grid, st, RING_ARGS)) \
                                   : (fix ? launch_ring<true, false, S_, B_>(grid, st, RING_ARGS) : launch_ring<false, false, S_, B_>(grid, st, RING_ARGS)))
-        const cudaError_t e = path == 1 ? RING_RUN(3, 4) : path == 2 ? RING_RUN(4, 3) : RING_RUN(2, 4);
+#define BULK_RUN(P_, N_, B_) (neg_idx ? (fix ? launch_bulk<true, true, P_, N_, B_>(grid, st, RING_ARGS) : launch_bulk<false, true, P_, N_, B_>(grid, st, RING_ARGS)) \
+                                     : (fix ? launch_bulk<true, false, P_, N_, B_>(grid, st, RING_ARGS) : launch_bulk<false, false, P_, N_, B_>(grid, st, RING_ARGS)))
+        const cudaError_t e = path == 1 ? RING_RUN(2, 4) : BULK_RUN(2, 1, 4);
+#undef BULK_RUN
 #undef RING_RUN
 #undef RING_ARGS
         if (e != cudaSuccess) { css_set_error("css_score_ce: ring launch: %s", cudaGetErrorString(e)); return (int)e; }

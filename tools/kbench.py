@@ -146,7 +146,7 @@ def main():
     res["class_stats (+reduce)"] = timeit(stream, a.iters)
     res["rep_rows only (ori flow)"] = timeit(lambda i: (css_b200.ops.rep_norms_nhwc if nhwc else css_b200.ops.rep_rows)(rep_all[i % P]), a.iters)
     res["proto_ema (+cdf)"] = timeit(ema, a.iters)
-    for path, name in ((0, "register kernel"), (1, "ring 3x4"), (2, "ring 4x3"), (3, "ring 2x4")):
+    for path, name in ((0, "register kernel"), (1, "ring 2 stages"), (2, "register/bulk hybrid")):
         if rows_dt == 0:
             lib.css_set_scorer_path(path)
             res[f"score_ce fwd+grad, {name} (not in path sum)"] = timeit(score, a.iters)
