@@ -280,11 +280,21 @@ def _generate_cut_gather(image, labels, confs, mode):
     total = batch_size * world
     boxes = class_sets = None
     if mode == 'classmix':
-        # the reference draws a permutation for every gathered image; the draws for other ranks' images need their label
-        # maps, which only the gather provides -- single-process groups and rank-local draws are supported here
+        # every rank draws torch.randperm(number of label values present) for EVERY gathered image, in gathered order
+        # (VOC.py:381,423,465 -> :511-516).  What the draws for other ranks' images need from those ranks is only that number (it
+        # fixes how much of the CPU generator's stream a permutation consumes), so one all_gather of `batch_size` counts replaces
+        # the gather of the label maps; this rank's own images get their real draws at their place in the sequence.
+        own = range(rank * batch_size, (rank + 1) * batch_size)
         if world > 1:
-            raise RuntimeError("css_b200: classmix across ranks needs the gathered label maps; use the reference path")
-        class_sets = [draw_class_set(labels[0][i]) for i in range(batch_size)]
+            n_all = [None] * world                                # a few ints per rank: backend-agnostic object gather
+            dist.all_gather_object(n_all, [int(torch.unique(labels[0][i]).numel()) for i in range(batch_size)])
+            counts = [n for per_rank in n_all for n in per_rank]
+        class_sets = []
+        for i in range(total):
+            if i in own:
+                class_sets.append(draw_class_set(labels[0][i - rank * batch_size]))
+            else:
+                torch.randperm(int(counts[i]))                    # advance the generator exactly as the reference does
     else:
         ratio = 2
         drawn = [draw_cut_box(H, W, ratio) for _ in range(total)]      # every rank draws for the whole gathered batch

@@ -275,7 +275,7 @@ def cut_case(name, *, maps, mode, B, C, H, W, seed):
     print(f"  {name}: boxes {boxes.tolist()}")
 
 
-def _cut_world2_worker(rank, port, out):
+def _cut_world2_worker(rank, port, out, mode):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -283,33 +283,48 @@ def _cut_world2_worker(rank, port, out):
     load_reference()
     import generalframeworks.dataset_helpers.VOC as V
     image, l1, _, c1, c2 = _aug_inputs(3, 21, 33, 37, 300 + rank, True)
+    if mode == "classmix":      # a different number of label values per image and rank: the permutation draws differ in length
+        for i in range(l1.shape[0]):
+            l1[i] = torch.where(l1[i] >= 0, l1[i] % (4 + 3 * i + 7 * rank), l1[i])
     _seed_all(31)                                     # the scripts seed every rank alike (args.seed)
-    r = V.generate_cut_gather_2(image.clone(), l1.clone(), c1.clone(), c2.clone(), mode="cutmix")
+    r = V.generate_cut_gather_2(image.clone(), l1.clone(), c1.clone(), c2.clone(), mode=mode)
     out[rank] = dict(image=_np(image), label0=_np(l1).astype(np.int16), conf0=_np(c1), conf1=_np(c2), out_image=_np(r[0]),
                      out_label0=_np(r[1]).astype(np.int16), out_conf0=_np(r[2]), out_conf1=_np(r[3]))
     dist.destroy_process_group()
 
 
-def cut_world2_case(name):
+def cut_world2_case(name, mode="cutmix", port=29641):
     """generate_cut_gather_2 of the reference on a TWO-process gloo group (VOC.py:393-434): pins that the partner index
-    (i + 1) % batch_size lands in rank 0's slice of the gathered batch and that every rank draws boxes for all gathered images."""
+    (i + 1) % batch_size lands in rank 0's slice of the gathered batch and that every rank draws boxes (cutmix) / class
+    permutations (classmix) for all gathered images, in gathered order."""
     import torch.multiprocessing as mp
     from css_b200 import aug
     from oracle import css_oracle as O
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_cut_world2_worker, args=(29641, out), nprocs=2, join=True)
-    d = dict(seed=31, mode="cutmix")
+    mp.spawn(_cut_world2_worker, args=(port, out, mode), nprocs=2, join=True)
+    d = dict(seed=31, mode=mode)
     B, _, H, W = out[0]["image"].shape
     for rank in (0, 1):
         _seed_all(31)
-        boxes = np.asarray([aug.draw_cut_box(H, W, 2) for _ in range(2 * B)], np.int32)[rank * B:(rank + 1) * B]
         own, r0 = out[rank], out[0]
-        o = O.cut_mix(own["image"], [own["label0"].astype(np.int64)], [own["conf0"], own["conf1"]], "cutmix", boxes=boxes,
+        boxes = np.zeros((B, 4), np.int32)
+        sets = np.full((B, 64), -100, np.int32)
+        if mode == "classmix":
+            for i in range(2 * B):
+                src = out[i // B]["label0"][i % B].astype(np.int64)
+                chosen = aug.draw_class_set(torch.from_numpy(src))          # the reference's draw for gathered image i
+                if i // B == rank:
+                    sets[i % B, :len(chosen)] = chosen
+        else:
+            boxes = np.asarray([aug.draw_cut_box(H, W, 2) for _ in range(2 * B)], np.int32)[rank * B:(rank + 1) * B]
+        o = O.cut_mix(own["image"], [own["label0"].astype(np.int64)], [own["conf0"], own["conf1"]], mode, boxes=boxes,
+                      class_sets=[[v for v in row if v != -100] for row in sets],
                       partner=(r0["image"], [r0["label0"].astype(np.int64)], [r0["conf0"], r0["conf1"]]))
         assert np.array_equal(o[0], own["out_image"]) and np.array_equal(o[1][0], own["out_label0"].astype(np.int64))
         assert np.array_equal(o[2][0], own["out_conf0"]) and np.array_equal(o[2][1], own["out_conf1"])
         d[f"r{rank}_boxes"] = boxes
+        d[f"r{rank}_class_sets"] = sets
         for k, v in own.items():
             d[f"r{rank}_{k}"] = v
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
@@ -372,6 +387,7 @@ def main():
     cut_case("cut_cutout_1", maps=1, mode="cutout", B=3, C=21, H=33, W=37, seed=23)
     cut_case("cut_classmix_2", maps=2, mode="classmix", B=3, C=21, H=33, W=37, seed=24)
     cut_world2_case("cut_cutmix_2_world2")
+    cut_world2_case("cut_classmix_2_world2", mode="classmix", port=29643)
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ from tests.helpers import load_golden
 AUG = ["aug_t2_scale", "aug_t2_flip", "aug_t3_city", "aug_t1_ori"]
 CUT = ["cut_cutmix_2", "cut_cutmix_3", "cut_cutout_1", "cut_classmix_2"]
 CUT_WORLD2 = "cut_cutmix_2_world2"          # generate_cut_gather_2 of the reference on a two-process group
+CLASSMIX_WORLD2 = "cut_classmix_2_world2"   # the same with mode='classmix' and a different number of label values per image
 
 
 def seed_all(seed):
@@ -68,6 +69,35 @@ def test_oracle_cut_mix_two_ranks_vs_reference():
         np.testing.assert_array_equal(boxes, g[f"r{rank}_boxes"])
         o = O.cut_mix(g[f"r{rank}_image"], [g[f"r{rank}_label0"].astype(np.int64)], [g[f"r{rank}_conf0"], g[f"r{rank}_conf1"]],
                       "cutmix", boxes=boxes, partner=part)
+        np.testing.assert_array_equal(o[0], g[f"r{rank}_out_image"])
+        np.testing.assert_array_equal(o[1][0], g[f"r{rank}_out_label0"].astype(np.int64))
+        np.testing.assert_array_equal(o[2][0], g[f"r{rank}_out_conf0"])
+        np.testing.assert_array_equal(o[2][1], g[f"r{rank}_out_conf1"])
+
+
+def test_oracle_class_mix_two_ranks_vs_reference():
+    """ClassMix on two ranks (VOC.py:423 -> :511-516): every rank draws one torch.randperm per GATHERED image, in gathered order.
+    A rank needs only the NUMBER of label values present in the other ranks' images to stay in step with the generator -- the
+    rule css_b200.aug follows (an all_gather of counts instead of label maps)."""
+    import torch
+    from css_b200 import aug
+    g = load_golden(CLASSMIX_WORLD2)
+    B = g["r0_image"].shape[0]
+    part = (g["r0_image"], [g["r0_label0"].astype(np.int64)], [g["r0_conf0"], g["r0_conf1"]])
+    counts = [len(np.unique(g[f"r{i // B}_label0"][i % B])) for i in range(2 * B)]
+    assert len(set(counts)) > 2, "the bundle should exercise permutations of different lengths"
+    for rank in (0, 1):
+        seed_all(int(g["seed"]))
+        sets = []
+        for i in range(2 * B):
+            if i // B == rank:
+                sets.append(aug.draw_class_set(torch.from_numpy(g[f"r{rank}_label0"][i % B].astype(np.int64))))
+            else:
+                torch.randperm(counts[i])
+        rec = [[v for v in row if v != -100] for row in g[f"r{rank}_class_sets"]]
+        assert sets == rec
+        o = O.cut_mix(g[f"r{rank}_image"], [g[f"r{rank}_label0"].astype(np.int64)], [g[f"r{rank}_conf0"], g[f"r{rank}_conf1"]],
+                      "classmix", class_sets=sets, partner=part)
         np.testing.assert_array_equal(o[0], g[f"r{rank}_out_image"])
         np.testing.assert_array_equal(o[1][0], g[f"r{rank}_out_label0"].astype(np.int64))
         np.testing.assert_array_equal(o[2][0], g[f"r{rank}_out_conf0"])

@@ -117,14 +117,14 @@ def test_peer_memory_allreduce_world2():
         assert out[rank]["graph_errs"] == [0.0] * 3, out[rank]
 
 
-def _cutmix_worker(rank, world, port, out):
+def _cutmix_worker(rank, world, port, out, mode="cutmix"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.cuda.set_device(0)
     import random
     from css_b200 import aug
-    g = load_golden("cut_cutmix_2_world2")          # recorded from the reference's generate_cut_gather_2 on two ranks
+    g = load_golden(f"cut_{mode}_2_world2")          # recorded from the reference's generate_cut_gather_2 on two ranks
     seed = int(g["seed"])
     random.seed(seed)
     np.random.seed(seed)
@@ -134,18 +134,21 @@ def _cutmix_worker(rank, world, port, out):
         t = torch.from_numpy(g[f"r{rank}_{k}"]).cuda()
         return t.to(dtype) if dtype is not None else t
 
-    got = aug.generate_cut_gather_2(dev("image"), dev("label0", torch.int64), dev("conf0"), dev("conf1"), mode="cutmix")
+    got = aug.generate_cut_gather_2(dev("image"), dev("label0", torch.int64), dev("conf0"), dev("conf1"), mode=mode)
     ok = all(np.array_equal(a.cpu().numpy(), g[f"r{rank}_{k}"].astype(a.cpu().numpy().dtype))
              for a, k in zip(got, ("out_image", "out_label0", "out_conf0", "out_conf1")))
     out[rank] = bool(ok) and got[1].dtype == torch.int64
     dist.destroy_process_group()
 
 
-def test_generate_cut_gather_world2_uses_rank0_partners():
-    port = 29700 + (os.getpid() % 90)
+@pytest.mark.parametrize("mode", ["cutmix", "classmix"])
+def test_generate_cut_gather_world2_uses_rank0_partners(mode):
+    """Two ranks: partners are rank 0's images; boxes (cutmix) and class permutations (classmix: only the other rank's counts of
+    label values travel) are drawn for every gathered image in the reference's order -- outputs equal the reference's recorded ones."""
+    port = 29700 + (os.getpid() % 90) + (100 if mode == "classmix" else 0)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_cutmix_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_cutmix_worker, args=(2, port, out, mode), nprocs=2, join=True)
     assert out[0] and out[1]
 
 
