@@ -88,7 +88,8 @@ def main():
             name = r["kernel"]
             key = name.split("(")[0].split("<")[0].strip().split(" ")[-1]
             if key == "rep_pass_kernel":
-                key = "rep_pass_student" if ("true" in name.split("<")[1].split(">")[0].split(",")[1] if "<" in name else False) else "rep_pass_teacher"
+                rows_arg = name.split("<")[1].split(">")[0].split(",")[1].strip() if "<" in name else "0"     # ROWS template argument
+                key = "rep_pass_student" if rows_arg in ("true", "1") else "rep_pass_teacher"
             agg.setdefault(key, []).append(to_bytes(r[rd[0]], unit_r) + to_bytes(r[wr[0]], unit_w))
         for k, v in agg.items():
             wl[k] = int(sum(v) / len(v))
