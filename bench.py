@@ -556,15 +556,22 @@ def main():
         wait_us = None
         if comm0 is not None:
             calls = max(comm1["calls"] - comm0["calls"], 1)
-            w_mine = torch.tensor([(comm1["wait_ns_total"] - comm0["wait_ns_total"]) / calls / 1e3], device=dev, dtype=torch.float64)
+            w_mine = torch.tensor([(comm1[k] - comm0[k]) / calls / 1e3 for k in ("wait_ns_total", "push_ns_total", "kernel_ns_total")],
+                                  device=dev, dtype=torch.float64)
             w_all = [torch.zeros_like(w_mine) for _ in range(world)]
             dist.all_gather(w_all, w_mine)
-            wait_us = [round(float(x.item()), 2) for x in w_all]
+            wait_us = [round(float(x[0].item()), 2) for x in w_all]
+            push_us = [round(float(x[1].item()), 2) for x in w_all]
+            kern_us = [round(float(x[2].item()), 2) for x in w_all]
         s_ = sorted(per_rank_ms)
         multi = {"per_rank_ms_per_step": {"min": s_[0], "median": s_[len(s_) // 2], "max": s_[-1]},
                  "exchange_wait_us_per_step_by_rank": wait_us,
+                 "exchange_push_us_per_step_by_rank": push_us if wait_us is not None else None,
+                 "exchange_kernel_us_per_step_by_rank": kern_us if wait_us is not None else None,
                  "note": "every rank times the same K steps with its own events; the step time reported is the max; "
-                         "exchange_wait = time the peer-memory kernel spent waiting for the slowest rank's block (rank skew)"}
+                         "exchange_wait = time the peer-memory kernel spent waiting for the slowest rank's block (rank skew), "
+                         "exchange_push = kernel entry until its own block is stored on every peer and fenced, exchange_kernel = whole "
+                         "kernel (globaltimer inside css_stats_allreduce)"}
 
     # ---- the step as the UNMODIFIED scripts drive it: DistributedDataParallel(find_unused_parameters=True) clones rep_all, the
     # loss verifies the carried rows on the device (css_rows_refresh) instead of re-reading the map ---------------------------

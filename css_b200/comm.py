@@ -72,11 +72,11 @@ class PeerStatsReducer:
         return _lib.load().css_comm_timeouts(self.local) if self.local is not None else 0
 
     def stats(self):
-        """dict(calls, timeouts, wait_ns_total): blocking device read, for diagnostics outside timed regions."""
-        out = (ctypes.c_ulonglong * 3)()
+        """dict(calls, timeouts, wait_ns_total, push_ns_total, kernel_ns_total): blocking device read, for diagnostics outside timed regions."""
+        out = (ctypes.c_ulonglong * 5)()
         with torch.cuda.device(self.device):
             check(_lib.load().css_comm_stats(self.local, out), "css_comm_stats")
-        return dict(calls=int(out[0]), timeouts=int(out[1]), wait_ns_total=int(out[2]))
+        return dict(calls=int(out[0]), timeouts=int(out[1]), wait_ns_total=int(out[2]), push_ns_total=int(out[3]), kernel_ns_total=int(out[4]))
 
     def allreduce(self, class_stats, C, D):
         lib = _lib.load()

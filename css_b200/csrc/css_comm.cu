@@ -3,17 +3,22 @@
 // map (loss.py:77,81; ddp_model.py:241-250: ~116 MB per rank) and, on one NVSwitch node, the NCCL all-reduce of the block.
 //
 // Every rank owns one communication buffer (cudaMalloc'ed by css_comm_alloc, exported with a CUDA IPC handle, mapped by its
-// peers).  One launch, one CTA:
-//   push   this rank's block is stored into slot[parity][rank] of EVERY peer's buffer (remote stores over NVLink),
-//   signal after a system-scope fence, flag[parity][rank] = epoch on every peer,
-//   wait   until the own buffer holds the flags of all ranks for this epoch (bounded spin: css_comm_set_timeout_ms, default
-//          10 minutes like the NCCL watchdog; on expiry the block is left as the LOCAL statistics -- never poisoned -- and the
-//          event is counted in a host-visible status word that css_comm_timeouts() reads without synchronising),
-//   sum    the slots are added in RANK ORDER, so every rank gets bit-identical statistics (NCCL's order depends on the
-//          algorithm it picks) and the prototypes cannot drift apart between ranks.
-// The epoch lives in the buffer and is bumped by the kernel, so a captured CUDA graph replays correctly.  Slots alternate
-// with the epoch's parity: a rank can only be one call ahead of a peer, because completing call e needs that peer's flag of
-// call e, which it raises only from inside its own call e.
+// peers).  One launch of `world` CTAs; CTA j serves peer (rank + j) % world and slice j of the block:
+//   push   the block is read into registers (one L2 round trip) and stored into slot[parity][rank] of the CTA's peer (remote
+//          stores over NVLink, one SM per peer so the stores of all peers stream out concurrently),
+//   signal after a system-scope fence, flag[parity][rank] = epoch on that peer,
+//   wait   until the own buffer holds the flags of all ranks for this epoch and every local CTA has read the block (bounded spin:
+//          css_comm_set_timeout_ms, default 10 minutes like the NCCL watchdog; on expiry nothing is poisoned -- a CTA that gives up
+//          leaves its slice of class_stats as the LOCAL statistics -- and the event is counted in a host-visible status word that
+//          css_comm_timeouts() reads without synchronising),
+//   sum    the CTA adds its slice of the slots in RANK ORDER, so every rank gets bit-identical statistics (NCCL's order depends
+//          on the algorithm it picks) and the prototypes cannot drift apart between ranks.
+// Measured on 8 B200 (V321): the first version (one CTA, a dependent L2 round trip per element in the push
+// and the sum loops) cost ~30 us per step, one CTA with the loads batched 18 us (7.5 us of it issuing the stores to seven peers
+// from one SM); an LL-style version ({value, epoch} pairs, no fence, polling every pair) 33 us.
+// The epoch lives in the buffer and is bumped by the last CTA of the launch, so a captured CUDA graph replays correctly.  Slots
+// alternate with the epoch's parity: a rank can only be one call ahead of a peer, because completing call e needs that peer's flag
+// of call e, which it raises only from inside its own call e.
 #include <cstring>
 
 #include "css_common.cuh"
@@ -21,6 +26,7 @@
 #define COMM_MAX_WORLD 16
 #define COMM_SLOT_FLOATS (CSS_CMAX * (CSS_D + 1))
 #define COMM_THREADS 1024
+#define COMM_PER_THREAD ((COMM_SLOT_FLOATS + COMM_THREADS - 1) / COMM_THREADS + ((COMM_SLOT_FLOATS + COMM_THREADS - 1) / COMM_THREADS) % 2)   // even
 #define COMM_TIMEOUT_DEFAULT_MS 600000ull      // a rank may legitimately be seconds late (checkpoint write, loader respawn, GC)
 
 struct CommHeader {
@@ -29,7 +35,11 @@ struct CommHeader {
     unsigned int timeouts;                    // number of calls that gave up waiting
     unsigned int* host_status;                // pinned, mapped: [0] = timeouts, mirrored so the host can poll without a sync
     unsigned long long wait_ns;               // total time the calls spent waiting for the slowest peer (css_comm_stats)
-    unsigned int pad[26];
+    unsigned long long push_ns;               // total time from kernel entry until the pushed block was fenced (remote stores acknowledged)
+    unsigned long long total_ns;              // total time inside the kernel
+    unsigned int loaded;                      // local CTAs that have read class_stats in this call (the sums overwrite it in place)
+    unsigned int ticket;                      // local CTAs that have finished this call: the last one bumps the epoch, resets both
+    unsigned int pad[20];
 };
 static_assert(sizeof(CommHeader) == 256, "CommHeader layout");
 
@@ -47,67 +57,107 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int WMAX>
 __global__ void __launch_bounds__(COMM_THREADS) stats_allreduce_kernel(float* __restrict__ class_stats, void* local, void* const* __restrict__ peers,
                                                                        int rank, int world, int n, unsigned long long timeout_ns) {
     css_pdl_enter();
-    __shared__ unsigned int s_epoch;
     __shared__ int s_ok;
     __shared__ unsigned long long s_wait;
     CommHeader* me = reinterpret_cast<CommHeader*>(local);
+    const unsigned long long t_enter = global_ns();
+    const int cta = blockIdx.x, peer_id = (rank + cta) % world;        // CTA 0 fills the own buffer's slot
+    // the epoch, the peer's address and the block are independent reads: all in flight together (one L2 round trip, not three).
+    // Every thread reads the epoch itself (a broadcast load); it is bumped only after every CTA of this launch has finished.
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
+    void* const peer_buf = peers[peer_id];
+    float own[COMM_PER_THREAD];            // thread t owns elements t, t + 1024, ...
+#pragma unroll
+    for (int j = 0; j < COMM_PER_THREAD; ++j) {
+        const int i = threadIdx.x + j * COMM_THREADS;
+        own[j] = (i < n) ? class_stats[i] : 0.f;
+    }
     if (threadIdx.x == 0) {
-        s_epoch = me->epoch + 1;
         s_ok = 1;
         s_wait = 0ull;
     }
-    __syncthreads();
-    const unsigned int epoch = s_epoch;
     const int parity = (int)(epoch & 1u);
-    // push: warp w serves peer w % world; the 32 / world warps of a peer interleave over the block
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = COMM_THREADS / 32;
     {
-        const int p = warp % world, sub = warp / world, share = n_warps / world;      // `share` warps split the block for one peer
-        if (sub < share) {
-            float* dst = comm_slot(peers[p], world, parity, rank);
-            for (int i = sub * 32 + lane; i < n; i += share * 32) dst[i] = class_stats[i];
+        float* dst = comm_slot(peer_buf, world, parity, rank);
+#pragma unroll
+        for (int j = 0; j < COMM_PER_THREAD; ++j) {
+            const int i = threadIdx.x + j * COMM_THREADS;
+            if (i < n) dst[i] = own[j];
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-        CommHeader* peer = reinterpret_cast<CommHeader*>(peers[threadIdx.x]);
+    __syncthreads();                      // every thread's loads have returned and its stores are issued
+    unsigned long long t_pushed = 0ull;
+    if (threadIdx.x == 0) {
+        atomicAdd(&me->loaded, 1u);       // this CTA no longer needs class_stats
+        // ONE system-scope fence per CTA: it is cumulative over the barrier above, so the whole CTA's stores are ordered before
+        // the flag (1024 fences, one per thread, cost several microseconds and add nothing)
+        __threadfence_system();
+        CommHeader* peer = reinterpret_cast<CommHeader*>(peer_buf);
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peer->flags[parity][rank]), "r"(epoch) : "memory");
-        // wait for rank `threadIdx.x`'s block to have landed here
-        const unsigned int* f = &me->flags[parity][threadIdx.x];
+        t_pushed = global_ns();
+    }
+    // wait: thread r < world for rank r's block to have landed here, thread `world` for the local CTAs to have read class_stats
+    if (threadIdx.x <= world) {
+        const unsigned int* f = (threadIdx.x < world) ? &me->flags[parity][threadIdx.x] : &me->loaded;
+        const unsigned int want = (threadIdx.x < world) ? epoch : (unsigned int)world;
         const unsigned long long t0 = global_ns();
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v == epoch) break;
+        while (ld_acquire_sys(f) != want) {
             if (global_ns() - t0 > timeout_ns) {
                 s_ok = 0;
                 break;
             }
-        } while (true);
+        }
         atomicMax(&s_wait, global_ns() - t0);
     }
     __syncthreads();
     const bool ok = s_ok != 0;
     if (ok) {
-        for (int i = threadIdx.x; i < n; i += COMM_THREADS) {
+        // this CTA's slice, summed in rank order; all ranks' values of an element are in flight together (L2: written remotely)
+        const int chunk = (n + world - 1) / world, lo = cta * chunk, hi = min(n, lo + chunk);
+        const float* slot0 = comm_slot(local, world, parity, 0);
+        for (int i = lo + threadIdx.x; i < hi; i += COMM_THREADS) {
+            float v[WMAX];
+#pragma unroll
+            for (int p = 0; p < WMAX; ++p) v[p] = (p < world) ? __ldcg(slot0 + (size_t)p * COMM_SLOT_FLOATS + i) : 0.f;
             float s = 0.f;
-            for (int p = 0; p < world; ++p) s += __ldcg(comm_slot(local, world, parity, p) + i);     // L2: the slots were written remotely
+#pragma unroll
+            for (int p = 0; p < WMAX; ++p)
+                if (p < world) s += v[p];
             class_stats[i] = s;
         }
-    }   // else: a peer never arrived -- class_stats keeps this rank's own statistics (a valid, rank-local prototype update)
+    }   // else: a peer never arrived -- this slice of class_stats keeps the rank's own statistics (valid, rank-local)
+    __syncthreads();
     if (threadIdx.x == 0) {
-        me->epoch = epoch;
-        me->wait_ns += s_wait;
-        if (!ok) {
-            me->timeouts += 1;
-            if (me->host_status) {
-                *reinterpret_cast<volatile unsigned int*>(me->host_status) = me->timeouts;
-                __threadfence_system();
+        if (cta == 0) {                   // diagnostics from the CTA that serves the own buffer
+            me->wait_ns += s_wait;
+            me->push_ns += t_pushed - t_enter;
+            me->total_ns += global_ns() - t_enter;
+        }
+        if (!ok) atomicAdd(&me->timeouts, 0x10000u);          // high half: CTAs that gave up in this call
+        __threadfence();
+        if (atomicAdd(&me->ticket, 1u) == (unsigned int)world - 1u) {      // last CTA of the launch
+            __threadfence();
+            const unsigned int t = *reinterpret_cast<volatile unsigned int*>(&me->timeouts);
+            if (t >> 16) {                 // one timed-out CALL, however many CTAs gave up
+                me->timeouts = (t & 0xffffu) + 1u;
+                if (me->host_status) {
+                    *reinterpret_cast<volatile unsigned int*>(me->host_status) = me->timeouts;
+                    __threadfence_system();
+                }
             }
+            me->loaded = 0u;
+            me->ticket = 0u;
+            me->epoch = epoch;
         }
     }
 }
@@ -172,9 +222,11 @@ extern "C" int css_comm_free(void* buffer) {
     return 0;
 }
 
-// diagnostics of a local buffer: out[0] = completed calls (epoch), out[1] = timeouts, out[2] = total ns spent waiting for peers.
+// diagnostics of a local buffer: out[0] = completed calls (epoch), out[1] = timeouts, out[2] = total ns spent waiting for peers,
+// out[3] = total ns from kernel entry to the fenced push, out[4] = total ns inside the kernel.
 // Reads device memory with a blocking copy: never call it inside a timed region.
-extern "C" int css_comm_stats(void* buffer, unsigned long long* out3_host) {
+extern "C" int css_comm_stats(void* buffer, unsigned long long* out5_host) {
+    unsigned long long* out3_host = out5_host;
     CSS_CHECK_ARG(buffer && out3_host && comm_find(buffer) >= 0, CSS_E_ARG, "css_comm_stats: not a buffer of css_comm_alloc");
     CommHeader h;
     cudaError_t e = cudaMemcpy(&h, buffer, sizeof(h), cudaMemcpyDeviceToHost);
@@ -182,6 +234,8 @@ extern "C" int css_comm_stats(void* buffer, unsigned long long* out3_host) {
     out3_host[0] = h.epoch;
     out3_host[1] = h.timeouts;
     out3_host[2] = h.wait_ns;
+    out5_host[3] = h.push_ns;
+    out5_host[4] = h.total_ns;
     return 0;
 }
 
@@ -226,8 +280,13 @@ extern "C" int css_stats_allreduce(float* class_stats, void* local_buffer, void*
     CSS_CHECK_ARG(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world, CSS_E_ARG, "css_stats_allreduce: bad rank %d / world %d",
                   rank, world);
     if (int e = css_check_dims(C, D)) return e;
-    css_launch(stats_allreduce_kernel, dim3(1), dim3(COMM_THREADS), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), class_stats, local_buffer, peer_buffers, rank, world, C * (D + 1),
-                                                                         g_timeout_ms * 1000000ull);
+    const int n = C * (D + 1);
+    const unsigned long long t_ns = g_timeout_ms * 1000000ull;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (world <= 2) css_launch(stats_allreduce_kernel<2>, dim3(world), dim3(COMM_THREADS), (size_t)0, st, class_stats, local_buffer, peer_buffers, rank, world, n, t_ns);
+    else if (world <= 4) css_launch(stats_allreduce_kernel<4>, dim3(world), dim3(COMM_THREADS), (size_t)0, st, class_stats, local_buffer, peer_buffers, rank, world, n, t_ns);
+    else if (world <= 8) css_launch(stats_allreduce_kernel<8>, dim3(world), dim3(COMM_THREADS), (size_t)0, st, class_stats, local_buffer, peer_buffers, rank, world, n, t_ns);
+    else css_launch(stats_allreduce_kernel<COMM_MAX_WORLD>, dim3(world), dim3(COMM_THREADS), (size_t)0, st, class_stats, local_buffer, peer_buffers, rank, world, n, t_ns);
     CSS_CHECK_LAUNCH("css_stats_allreduce", 1);
     return 0;
 }

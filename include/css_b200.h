@@ -294,9 +294,10 @@ int css_cut_mix(const float* image, const int64_t* label_a, const int64_t* label
  */
 int css_comm_set_timeout_ms(unsigned long long ms);
 int css_comm_timeouts(void* buffer);
-/* diagnostics (blocking device read, never inside a timed region): out3_host = {completed calls, timeouts, total nanoseconds
- * the calls spent waiting for the slowest peer's block} */
-int css_comm_stats(void* buffer, unsigned long long* out3_host);
+/* diagnostics (blocking device read, never inside a timed region): out5_host = {completed calls, timeouts, total nanoseconds
+ * the calls spent waiting for the slowest peer's block, total ns from kernel entry until the pushed block was fenced, total ns
+ * inside the kernel} */
+int css_comm_stats(void* buffer, unsigned long long* out5_host);
 size_t css_comm_bytes(int world);
 int css_comm_alloc(int world, void** buffer);
 int css_comm_free(void* buffer);
