@@ -13,7 +13,8 @@
 // -------------------------------------------------------------------------------------------------------------------
 #define GSL_ELEMS 8192                       // floats per slab (32 KB)
 #define GSL_THREADS 256
-#define GSL_BATCH 8
+#define GSL_BATCH 24                         // anchor ids a thread has in flight while the image's list is built (V321: the whole scan is one round trip)
+#define GSL_PF_ANCH 3                        // listed anchors a thread may own on the pipelined path (3 x 256 per image)
 #define GSL_LIST_MAX 6144                    // anchors of one image kept in shared memory (more: the slab rescans the ids)
 
 __device__ __forceinline__ void slab_apply(float* __restrict__ slab, const float* __restrict__ grad_anchor, float go, int a, int s, int hw,
@@ -69,6 +70,54 @@ __global__ void __launch_bounds__(GSL_THREADS, 4) grad_slab_kernel(const float* 
     const int n_slabs = (img + GSL_ELEMS - 1) / GSL_ELEMS;
     for (int i = threadIdx.x; i < GSL_ELEMS / 4; i += GSL_THREADS) slab4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+    if (cnt <= GSL_THREADS * GSL_PF_ANCH && cnt <= list_cap && 2 * hw >= GSL_ELEMS) {
+        // Pipelined path (a thread owns <= GSL_PF_ANCH listed anchors; with hw >= half a slab an anchor has <= 2 channels inside a
+        // slab): the gradient values of the NEXT slab are fetched while the current slab streams out, so the L2 round trip of the
+        // anchor values is off the slab's critical path (it was serialised with the write-out: apply -> barrier -> write -> barrier).
+        float pv[GSL_PF_ANCH][2];
+        int po[GSL_PF_ANCH][2];
+        auto gather = [&](int j) {
+            const int r0 = j * GSL_ELEMS, r1 = min(r0 + GSL_ELEMS, img);
+            const int q0 = r0 / hw, m0 = r0 - q0 * hw, q1 = (r1 - 1) / hw, m1 = (r1 - 1) - q1 * hw;
+#pragma unroll
+            for (int u = 0; u < GSL_PF_ANCH; ++u) {
+                const int t = threadIdx.x + u * GSL_THREADS;
+                po[u][0] = po[u][1] = -1;
+                if (t < cnt) {
+                    const int a = list_a[t], sp = list_s[t];
+                    const int d_min = q0 + (sp < m0), d_max = q1 - (sp > m1);
+                    const float* ga = grad_anchor + (size_t)a * CSS_D;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (d_min + c <= d_max) {
+                            pv[u][c] = __ldg(ga + d_min + c);
+                            po[u][c] = (d_min + c) * hw + sp - r0;
+                        }
+                    }
+                }
+            }
+        };
+        int j = blockIdx.x;
+        if (j < n_slabs) gather(j);
+        for (; j < n_slabs; j += gridDim.x) {
+#pragma unroll
+            for (int u = 0; u < GSL_PF_ANCH; ++u)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (po[u][c] >= 0) atomicAdd(&slab[po[u][c]], go * pv[u][c]);
+            __syncthreads();
+            const int r0 = j * GSL_ELEMS, r1 = min(r0 + GSL_ELEMS, img);
+            if (j + (int)gridDim.x < n_slabs) gather(j + gridDim.x);          // in flight during the write-out below
+            float4* out4 = reinterpret_cast<float4*>(out_img + r0);
+            const int n4 = (r1 - r0) >> 2;
+            for (int i = threadIdx.x; i < GSL_ELEMS / 4; i += GSL_THREADS) {
+                if (i < n4) __stcs(out4 + i, slab4[i]);
+                slab4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+        }
+        return;
+    }
     for (int j = blockIdx.x; j < n_slabs; j += gridDim.x) {
         const int r0 = j * GSL_ELEMS, r1 = min(r0 + GSL_ELEMS, img);
         const int q0 = r0 / hw, m0 = r0 - q0 * hw, q1 = (r1 - 1) / hw, m1 = (r1 - 1) - q1 * hw;
