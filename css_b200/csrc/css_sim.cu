@@ -331,9 +331,9 @@ extern "C" int css_sim_map(const void* rep, int rep_dtype, const float* prototyp
 // css_rows_refresh: "are these pixel-major rows still the rows of THIS map?"  The student pass hands rows / norms to the loss
 // on the `prob` tensor; the reference wraps the model in DistributedDataParallel(find_unused_parameters=True)
 // (mix_label.py:77), whose output sink CLONES rep_all, so the loss sees equal content at another address.  Instead of
-// re-reading the whole map (the rows-only pass), a sampled comparison decides on the device: thread p compares RV_SAMPLES
-// channels of pixel p (64 apart, offset rotating with p, so every channel plane and every pixel is touched) bit for bit with
-// the carried rows and raises meta[CSS_META_ROWS_STALE]; the rows-only pass that follows returns at once unless that word is
+// re-reading the whole map (the rows-only pass), a sampled comparison decides on the device: RV_SAMPLES adjacent channels of
+// EVERY pixel (the channel quad rotating with warp and round, so every channel plane is touched) are compared bit for bit with
+// the carried rows, which raises meta[CSS_META_ROWS_STALE]; the rows-only pass that follows returns at once unless that word is
 // set.  No host synchronisation, graph-capturable.  The word is cleared by css_select, which therefore runs first.
 // ---------------------------------------------------------------------------------------------------------------
 #define RV_SAMPLES 4
@@ -341,18 +341,23 @@ template <typename T>
 __global__ void __launch_bounds__(256) rows_verify_kernel(const T* __restrict__ rep, const T* __restrict__ rows, int hw, int N,
                                                           int32_t* __restrict__ meta) {
     css_pdl_enter();
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= N) return;
-    const int b = p / hw, s = p - b * hw;
-    const int d0 = (int)(((unsigned)p * 37u) & (unsigned)(CSS_D / RV_SAMPLES - 1));
+    // A warp owns 32 consecutive pixels and checks them in RV_SAMPLES rounds of 8 pixels x 4 ADJACENT channels (lane l: pixel
+    // 8 i + l / 4, channel quad + l % 4): a round reads one 32-byte sector per pixel row and 4 planes x 32 bytes of the map -- 12
+    // sectors for 32 samples, against 64 when every lane picked its own channel.  The quad rotates with warp and round.
+    const int lane = threadIdx.x & 31, wbase = (blockIdx.x * 256 + threadIdx.x) & ~31;
+    const unsigned wq = (unsigned)(wbase >> 5) * RV_SAMPLES;
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < RV_SAMPLES; ++i) {
-        const int d = d0 + i * (CSS_D / RV_SAMPLES);
-        const T a = rep[((size_t)b * CSS_D + d) * hw + s];
-        const T r = rows[(size_t)p * CSS_D + d];
-        if constexpr (sizeof(T) == 4) bad |= __float_as_uint(a) != __float_as_uint(r);
-        else bad |= __bfloat16_as_ushort(a) != __bfloat16_as_ushort(r);
+        const int p = wbase + 8 * i + (lane >> 2);
+        const int d = 4 * (int)(((wq + i) * 37u) & (unsigned)(CSS_D / 4 - 1)) + (lane & 3);
+        if (p < N) {
+            const int b = p / hw, s = p - b * hw;
+            const T a = rep[((size_t)b * CSS_D + d) * hw + s];
+            const T r = rows[(size_t)p * CSS_D + d];
+            if constexpr (sizeof(T) == 4) bad |= __float_as_uint(a) != __float_as_uint(r);
+            else bad |= __bfloat16_as_ushort(a) != __bfloat16_as_ushort(r);
+        }
     }
     if (bad) meta[CSS_META_ROWS_STALE] = 1;
 }
