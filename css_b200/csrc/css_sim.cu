@@ -52,8 +52,27 @@ __global__ void __launch_bounds__(CSS_D) proto_prep_kernel(const float* __restri
 // A warp reads 2 x 64 contiguous bytes per (channel pair, pixel group); the 4 warps of a CTA cover adjacent pixels.
 // ---------------------------------------------------------------------------------------------------------------
 // rep element loaders: fp32, or bf16 widened exactly to fp32 (all arithmetic stays fp32)
-__device__ __forceinline__ float ld_elem(const float* p) { return ldg_stream(p); }
-__device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) {
+// The map is read exactly once: its lines are marked evict-first in L2 so that they do not push out the pixel-major rows the same
+// kernel is writing (class sums and the scorer read those next): -5 us per V321 step.  Marking the row stores evict-last on top of
+// that was measured slower (student pass 68 -> 74 us, step +17 us).  CSS_B200_L2_HINT=0 at build time restores plain streaming loads.
+#ifndef CSS_B200_L2_HINT
+#define CSS_B200_L2_HINT 1
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ld_elem(const float* p, uint64_t pol) {
+#if CSS_B200_L2_HINT
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return ldg_stream(p);
+#endif
+}
+__device__ __forceinline__ float ld_elem(const __nv_bfloat16* p, uint64_t) {
     unsigned short u;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
     return __uint_as_float((uint32_t)u << 16);
@@ -89,6 +108,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ks = lane / PL, psub = lane % PL;
     const float4* myp = sp + (NG > 0 ? ks * SL : 0);
+    const uint64_t pol = l2_evict_first_policy();
     const int n_wchunks = (N + WP - 1) / WP;
     for (int wc = blockIdx.x * SM_WARPS + warp; wc < n_wchunks; wc += gridDim.x * SM_WARPS) {
         const T* x[SM_PPT];
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, SM_MINB) rep_pass_kernel(const 
 #pragma unroll
             for (int u = 0; u < SM_U; ++u)
 #pragma unroll
-                for (int j = 0; j < SM_PPT; ++j) v[u][j] = ld_elem(x[j] + (size_t)(d0 + u) * hw);
+                for (int j = 0; j < SM_PPT; ++j) v[u][j] = ld_elem(x[j] + (size_t)(d0 + u) * hw, pol);
             if (ROWS && sizeof(T) == 2) {
                 // bf16 map -> bf16 rows (lossless): the 16 channels a lane holds are 32 contiguous bytes = one whole sector
 #pragma unroll
