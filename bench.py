@@ -699,11 +699,14 @@ def main():
             prof = json.load(open(prof_path)).get(args.workload, {})
         except Exception:
             prof = {}
-    traffic = prof.get("score_ce_kernel")
+    scorer_env = os.environ.get("CSS_B200_SCORER", "bulk")          # the library's default path is the register / bulk-copy hybrid
+    scorer_kernel = {"reg": "score_ce_kernel", "ring": "score_ce_ring_kernel"}.get(scorer_env, "score_ce_bulk_kernel") \
+        if crit.last["rows"].dtype == torch.float32 else "score_ce_kernel"
+    traffic = prof.get(scorer_kernel)
     # ceiling of the access pattern, measured live on this device with the step's own pixel-major copy as the table
     probe = run_probe(crit.last["rows"], v_eff * Q if v_eff else Q, Nn)
     gather_peak = probe.get("l2_gather_gbs") if probe else None
-    roofline = {"bound": "l2_gather", "kernel": "score_ce_kernel (css_score_ce)", "achieved": achieved,
+    roofline = {"bound": "l2_gather", "kernel": f"{scorer_kernel} (css_score_ce)", "achieved": achieved,
                 "peak": gather_peak, "unit": "GB/s", "frac": (achieved / gather_peak) if gather_peak else None,
                 "peak_source": "measured live by tools/dev/css_probe.cu: random 1 KB-row gathers from this step's own pixel-major copy "
                                f"({crit.last['rows'].numel() * crit.last['rows'].element_size() / 1e6:.0f} MB table), no math, best of 3 "

@@ -208,10 +208,11 @@ int css_score_ce(const void* rows, int rows_dtype, const float* norms, const flo
                  float* loss_kq, int32_t* anchor_px, float* grad_anchor, float* loss, void* stream);
 
 /* fp32 rows with the gradient have three implementations of the same arithmetic: the register kernel (one candidate row per 8-lane
- * group in flight; default), a shared-memory ring fed by 16-byte cp.async copies, and a hybrid in which every other step of a warp
- * arrives through cp.async.bulk + mbarrier while the rest are register loads.  Measured on B200 (V321 / C768): 252 / 308 us,
- * 280 / 302 us, 244 / 310 us -- see DESIGN.md section 4.  css_set_scorer_path(0 | 1 | 2) selects one, -1 returns to the default /
- * the CSS_B200_SCORER=reg|ring|bulk environment variable.  The draws are identical on every path; the sums are taken in a different
+ * group in flight), a shared-memory ring fed by 16-byte cp.async copies, and a hybrid in which every other step of a warp arrives
+ * through cp.async.bulk + mbarrier while the rest are register loads (default).  Measured on B200 (V321 / C768 scorer alone):
+ * 252 / 308 us, 280 / 302 us, 244 / 310 us; over the configs[4] sweep the hybrid shortens the whole step by 2 % on average
+ * (DESIGN.md section 4).  css_set_scorer_path(0 | 1 | 2) selects one, -1 returns to the default / the
+ * CSS_B200_SCORER=reg|ring|bulk environment variable.  The draws are identical on every path; the sums are taken in a different
  * order (the positive first), so results agree to rounding, not bit for bit. */
 int css_set_scorer_path(int path);
 

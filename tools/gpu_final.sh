@@ -16,7 +16,7 @@ timeout 300 python tools/kbench.py --iters 20 --workload voc321_mix_nhwc > $OUT/
 timeout 600 python tools/sweep.py --out $OUT/${TAG}_sweep_1gpu.json > $OUT/${TAG}_sweep_1gpu.txt 2>&1; echo "sweep rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_launches.log 2>&1
-for k in rep_pass_kernel score_ce_kernel grad_slab_kernel upsample_label_fuse_kernel class_sums_kernel rows_verify_kernel; do
+for k in rep_pass_kernel score_ce grad_slab_kernel upsample_label_fuse_kernel class_sums_kernel rows_verify_kernel; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 3 -f -o $OUT/${TAG}_ncu_$k \
       python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu_$k.log 2>&1
 done
