@@ -56,3 +56,54 @@ def test_allreduce_replaces_allgather_world2():
         err, n_local, tot = out[rank]
         assert err < 1e-5, f"rank {rank}: prototypes differ from the all_gather semantics by {err}"
         assert n_local > 0 and tot == total_valid
+
+
+def _cut_worker(rank, world, port, out, mode):
+    """Host side of css_b200.aug.generate_cut_gather_2 on two ranks with CPU tensors: the device launch (aug.cut_mix, CUDA only)
+    is replaced by a recorder, everything before it -- who draws what from which generator, what is gathered, where the partners
+    come from -- runs as shipped."""
+    import random
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from css_b200 import aug
+    g = load_golden(f"cut_{mode}_2_world2")          # recorded from the reference's generate_cut_gather_2 on two ranks
+    seed = int(g["seed"])
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    seen = {}
+
+    def recorder(image, labels, confs, mode_, boxes=None, class_sets=None, partner=None):
+        seen.update(mode=mode_, boxes=boxes, class_sets=class_sets, partner=partner)
+        return image, labels, confs
+
+    real, aug.cut_mix = aug.cut_mix, recorder
+    try:
+        t = lambda k, dt=None: torch.from_numpy(g[f"r{rank}_{k}"]).to(dt) if dt else torch.from_numpy(g[f"r{rank}_{k}"])   # noqa: E731
+        aug.generate_cut_gather_2(t("image"), t("label0", torch.int64), t("conf0"), t("conf1"), mode=mode)
+    finally:
+        aug.cut_mix = real
+    ok = seen["mode"] == mode and seen["partner"] is not None
+    p_img, p_lab, p_conf = seen["partner"]
+    ok &= np.array_equal(p_img.numpy(), g["r0_image"]) and np.array_equal(p_lab[0].numpy(), g["r0_label0"].astype(np.int64))
+    ok &= np.array_equal(p_conf[0].numpy(), g["r0_conf0"]) and np.array_equal(p_conf[1].numpy(), g["r0_conf1"])
+    if mode == "classmix":
+        rec = [[int(v) for v in row if v != -100] for row in g[f"r{rank}_class_sets"]]
+        ok &= [list(s) for s in seen["class_sets"]] == rec
+    else:
+        ok &= np.array_equal(np.asarray(seen["boxes"]), g[f"r{rank}_boxes"])
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_cut_gather_world2_host_logic_cutmix_and_classmix():
+    """N > 1 host logic of the augmentation hand-off on CPU (gloo, world size 2): partners are broadcast from rank 0, every rank
+    draws boxes for all gathered images (CutMix), and for ClassMix only the per-image counts of label values are gathered while
+    the permutation draws stay in the reference's order -- checked against what two ranks of the reference recorded."""
+    for i, mode in enumerate(("cutmix", "classmix")):
+        port = 29100 + (os.getpid() % 300) + 400 * i
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_cut_worker, args=(2, port, out, mode), nprocs=2, join=True)
+        assert out[0] and out[1], f"{mode}: {dict(out)}"
